@@ -1,0 +1,139 @@
+/*
+ * qwen_cuda.h -- the C-ABI shim between qwen3.c's host code and the sm_100a kernels.
+ *
+ * Plain C types only (pointers, ints, sizes); no C++/torch types cross this line.
+ * The reference has no FFI of its own: its forward path is a set of C functions
+ * declared in include/forward.h, include/q8.h and include/model.h. libqwen3.so
+ * re-exports exactly those symbols (host C in qwen3.c_b200/csrc/host_*.c) and each
+ * of them is a thin call into one qwen_cuda_* entry point declared here. Each
+ * declaration names the reference interface it stands behind.
+ *
+ * Conventions: every function that can fail returns 0 on success and a negative
+ * code otherwise; qwen_cuda_last_error() returns a static, thread-local text for
+ * the last failure. Nothing falls back to the CPU: with no CUDA device,
+ * qwen_cuda_create() fails and the host layer reports it.
+ *
+ * "host" pointers are ordinary (or pinned) host memory; the shim stages them.
+ */
+#ifndef QWEN_CUDA_H
+#define QWEN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct QwenCudaCtx QwenCudaCtx; /* opaque device context */
+
+/* A Q8_0 tensor as it sits in the checkpoint mapping: numel int8 codes and
+ * numel/group fp32 scales (reference: include/q8.h:16-19, src/model.c:120-142). */
+typedef struct QwenCudaQ8 {
+    const int8_t* q;
+    const float* s;
+} QwenCudaQ8;
+
+/* Everything qwen_cuda_create needs, as host pointers into the checkpoint mapping.
+ * Mirrors ModelParams + ModelWeights (reference: include/model.h:30-82) without
+ * depending on those headers. Per-layer arrays have n_layers entries. */
+typedef struct QwenCudaModelDesc {
+    int dim, hidden_dim, n_layers, n_heads, n_kv_heads, vocab_size, seq_len, head_dim,
+        shared_classifier, group_size;
+    const float* att_rms_norm; /* [L][dim] */
+    const float* ffn_rms_norm; /* [L][dim] */
+    const float* out_rms_norm; /* [dim] */
+    const float* q_rms_norm;   /* [L][head_dim] */
+    const float* k_rms_norm;   /* [L][head_dim] */
+    QwenCudaQ8 emb;            /* [vocab][dim] */
+    QwenCudaQ8 cls;            /* [vocab][dim]; same pointers as emb when tied */
+    const QwenCudaQ8* wq;      /* [L] of [n_heads*head_dim][dim] */
+    const QwenCudaQ8* wk;      /* [L] of [n_kv_heads*head_dim][dim] */
+    const QwenCudaQ8* wv;
+    const QwenCudaQ8* wo;      /* [L] of [dim][n_heads*head_dim] */
+    const QwenCudaQ8* w1;      /* [L] of [hidden_dim][dim] */
+    const QwenCudaQ8* w2;      /* [L] of [dim][hidden_dim] */
+    const QwenCudaQ8* w3;
+    /* RoPE tables computed by the HOST with libm so they are the reference's values
+     * bit for bit (reference: src/forward.c:109-110): [seq_len][head_dim/2] each. */
+    const float* rope_cos;
+    const float* rope_sin;
+} QwenCudaModelDesc;
+
+/* Tensor-parallel placement of this context. tp_size 1 = whole model. */
+typedef struct QwenCudaTp {
+    int rank;
+    int size;
+} QwenCudaTp;
+
+/* ---- lifecycle ------------------------------------------------------------- */
+int qwen_cuda_device_count(void);
+const char* qwen_cuda_last_error(void);
+void qwen_cuda_clear_error(void);
+
+/* Stands behind model_create's weight + state setup (reference: src/model.c:162-282,
+ * 321-406): uploads every tensor of `desc` to `device`, repacks it into the kernels'
+ * layout, allocates the device KV cache and scratch. NULL on failure. */
+QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* desc, int device, QwenCudaTp tp);
+/* Stands behind model_free (reference: src/model.c:491-500). NULL-safe. */
+void qwen_cuda_destroy(QwenCudaCtx* ctx);
+
+/* Pinned host memory for state.logits (reference: src/model.c:342 callocs it). */
+void* qwen_cuda_host_alloc(size_t bytes);
+void qwen_cuda_host_free(void* p);
+
+/* ---- the decode step --------------------------------------------------------
+ * Stands behind forward() (reference: src/forward.c:225-350). Runs the step for
+ * (token, pos), then copies vocab_size logits to `logits_host` (pinned or not) and
+ * waits for them. */
+int qwen_cuda_forward(QwenCudaCtx* ctx, int token, int pos, float* logits_host);
+/* Same step, enqueue only: logits stay on the device (no copy, no wait). */
+int qwen_cuda_forward_async(QwenCudaCtx* ctx, int token, int pos);
+/* Copy the device logits of the last step to the host and wait. */
+int qwen_cuda_logits_to_host(QwenCudaCtx* ctx, float* logits_host);
+/* Greedy chain entirely on the device: n steps starting at (first_token, pos0); step i
+ * feeds the argmax (lowest index on ties) of step i-1. out_tokens_host[n] receives the
+ * n argmax tokens. Stands behind the completion loop's forward+sample pair when the
+ * sampler is greedy (reference: src/completion.c:57-66). */
+int qwen_cuda_decode_greedy(QwenCudaCtx* ctx, int first_token, int pos0, int n, int* out_tokens_host);
+/* Device-timed decode for bench.py: `warmup` untimed then `steps` timed steps at
+ * positions pos0, pos0+1, ... (token fixed), CUDA events on the context's stream.
+ * *ms_total = device milliseconds for the timed steps; *launches = kernels launched. */
+int qwen_cuda_time_decode(QwenCudaCtx* ctx, int token, int pos0, int steps, int warmup,
+                          float* ms_total, int* launches);
+int qwen_cuda_sync(QwenCudaCtx* ctx);
+/* 0 = persistent decode kernel (default), 1 = one kernel per op (debug / cross-check). */
+int qwen_cuda_set_path(QwenCudaCtx* ctx, int path);
+
+/* ---- KV cache access (test + long-context parity hooks) ----------------------
+ * Host side uses the reference's order: [npos][n_kv_heads*head_dim] for one layer
+ * (reference: src/model.c:353-361, src/forward.c:244-248). */
+int qwen_cuda_kv_write(QwenCudaCtx* ctx, int layer, int pos0, int npos, const float* k_host, const float* v_host);
+int qwen_cuda_kv_read(QwenCudaCtx* ctx, int layer, int pos0, int npos, float* k_host, float* v_host);
+/* Read back a device activation by name ("x", "q", "att", "h", "aq", "as") for layer-by-layer
+ * parity tests. Returns the number of elements copied or a negative code. */
+int qwen_cuda_debug_read(QwenCudaCtx* ctx, const char* what, void* host, size_t max_bytes);
+
+/* ---- single ops, host in / host out (context-free) ---------------------------
+ * Each stands behind the same-named function of include/forward.h / q8.h. */
+int qwen_cuda_q8_quantize(int8_t* q, float* s, const float* x, int n, int group);          /* q8.c:5-30 */
+int qwen_cuda_q8_dequantize(float* x, const int8_t* q, const float* s, int n, int group);  /* q8.c:32-37 */
+int qwen_cuda_matmul(float* out, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
+                     int n, int d, int group);                                           /* forward.c:79-101 */
+/* Test hook: the exact int32 dot of every (row, group), dots[d][n/group]. */
+int qwen_cuda_matmul_group_dots(int32_t* dots, const int8_t* xq, const int8_t* wq, int n, int d, int group);
+int qwen_cuda_rmsnorm(float* out, const float* x, const float* w, int size);                /* forward.c:12-28 */
+int qwen_cuda_softmax(float* x, int size);                                                  /* forward.c:34-77 */
+/* cos/sin: head_dim/2 host-computed values for this position (forward.c:109-110). */
+int qwen_cuda_rotary(float* x, int head_dim, const float* cos_host, const float* sin_host); /* forward.c:104-118 */
+int qwen_cuda_swiglu(float* x1, const float* x3, int size);                                 /* forward.c:134-139 */
+int qwen_cuda_silu(float* y, const float* x, int size, int sigmoid_only);                   /* forward.c:122-129 */
+/* Stands behind attention() (reference: src/forward.c:141-195): q_host is n_heads*head_dim
+ * floats (normalised + rotated), out_host receives n_heads*head_dim floats; K/V come from
+ * the device cache of `layer`, slots 0..pos. */
+int qwen_cuda_attention(QwenCudaCtx* ctx, int layer, int pos, const float* q_host, float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QWEN_CUDA_H */

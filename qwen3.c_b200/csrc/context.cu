@@ -1,0 +1,382 @@
+// context.cu -- device context: upload + repack of a checkpoint, KV cache, the
+// forward entry points of include/qwen_cuda.h. Stands behind model_create /
+// model_free / forward (reference: src/model.c:162-282, 321-406, 491-500;
+// src/forward.c:225-350).
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+int qw_attention_device(QwenCudaCtx* c, int layer, int pos, const float* q_dev, float* out_dev);
+int qw_decode_ops_launches(const QwenCudaCtx* c);
+int qw_decode_mega_launches(const QwenCudaCtx* c);
+
+namespace {
+
+template <typename T>
+int dev_alloc(T** p, size_t count, bool zero = true) {
+    QW_CUDA(cudaMalloc((void**) p, std::max<size_t>(count * sizeof(T), 16)));
+    if (zero) QW_CUDA(cudaMemset(*p, 0, std::max<size_t>(count * sizeof(T), 16)));
+    return 0;
+}
+
+int upload_f32(float** dst, const float* src, size_t n) {
+    if (dev_alloc(dst, n, false)) return -1;
+    QW_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Staging area for one checkpoint tensor (plain layout) on its way to the SG layout.
+struct Stage {
+    int8_t* q = nullptr;
+    float* s = nullptr;
+    size_t cap = 0; // in codes
+    ~Stage() {
+        if (q) cudaFree(q);
+        if (s) cudaFree(s);
+    }
+    int reserve(size_t codes) {
+        if (codes <= cap) return 0;
+        if (q) cudaFree(q);
+        if (s) cudaFree(s);
+        q = nullptr;
+        s = nullptr;
+        QW_CUDA(cudaMalloc((void**) &q, codes));
+        QW_CUDA(cudaMalloc((void**) &s, codes / 64 * 4 + 16));
+        cap = codes;
+        return 0;
+    }
+};
+
+// Upload rows [row0, row0+rows) of a [*, src_n] tensor and repack the column window
+// [col0, col0+n) into dst rows dst_row0 + r*dst_row_step.
+int put(Stage& st, const QwenCudaQ8& t, int src_n, int row0, int rows, int col0, int n, uint8_t* dst, int dst_row0,
+        int dst_row_step, cudaStream_t stream) {
+    const size_t codes = (size_t) rows * src_n;
+    if (st.reserve(codes)) return -1;
+    QW_CUDA(cudaMemcpyAsync(st.q, t.q + (size_t) row0 * src_n, codes, cudaMemcpyHostToDevice, stream));
+    QW_CUDA(cudaMemcpyAsync(st.s, t.s + (size_t) row0 * src_n / 64, codes / 64 * 4, cudaMemcpyHostToDevice, stream));
+    launch_repack(st.q, st.s, src_n, col0, n, rows, dst, dst_row0, dst_row_step, stream);
+    QW_CUDA(cudaGetLastError());
+    // the staging buffers are reused by the next tensor; pageable-source copies are
+    // already synchronous with respect to the host buffer, the kernel is stream ordered
+    return 0;
+}
+
+} // namespace
+
+extern "C" QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* m, int device, QwenCudaTp tp) {
+    if (!m) {
+        qw_set_error("qwen_cuda_create: null descriptor");
+        return nullptr;
+    }
+    if (qwen_cuda_device_count() <= device || device < 0) {
+        qw_set_error("qwen_cuda_create: CUDA device %d not available (%d visible); there is no CPU path", device,
+                     qwen_cuda_device_count());
+        return nullptr;
+    }
+    if (m->group_size != 64 || m->head_dim != 128) {
+        qw_set_error("qwen_cuda_create: only block_size 64 / head_dim 128 checkpoints are supported (got %d / %d)",
+                     m->group_size, m->head_dim);
+        return nullptr;
+    }
+    if (tp.size < 1 || tp.rank < 0 || tp.rank >= tp.size || m->n_kv_heads % tp.size || m->n_heads % tp.size
+        || m->vocab_size % tp.size || m->hidden_dim % (64 * tp.size) || m->dim % 64
+        || m->n_heads % m->n_kv_heads || (m->n_heads / m->n_kv_heads) > 8) {
+        qw_set_error("qwen_cuda_create: shape not divisible for tp=%d (heads %d/%d, hidden %d, vocab %d, dim %d)",
+                     tp.size, m->n_heads, m->n_kv_heads, m->hidden_dim, m->vocab_size, m->dim);
+        return nullptr;
+    }
+    QW_CUDA_NULL(cudaSetDevice(device));
+    QwenCudaCtx* c = new QwenCudaCtx();
+    memset(c, 0, sizeof *c);
+    c->device = device;
+    cudaDeviceProp prop;
+    QW_CUDA_NULL(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        qw_set_error("qwen_cuda_create: device is sm_%d%d, this library is built for sm_100a only", prop.major,
+                     prop.minor);
+        delete c;
+        return nullptr;
+    }
+    QW_CUDA_NULL(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    QW_CUDA_NULL(cudaEventCreate(&c->ev0));
+    QW_CUDA_NULL(cudaEventCreate(&c->ev1));
+
+    c->D = m->dim; c->Hd = m->hidden_dim; c->L = m->n_layers; c->H = m->n_heads; c->KVH = m->n_kv_heads;
+    c->V = m->vocab_size; c->S = m->seq_len; c->hd = m->head_dim; c->G = m->group_size;
+    c->tp_rank = tp.rank; c->tp_size = tp.size;
+    c->Hl = c->H / tp.size; c->KVHl = c->KVH / tp.size; c->Pl = c->Hl * 128; c->Kl = c->KVHl * 128;
+    c->Hdl = c->Hd / tp.size; c->Vl = c->V / tp.size;
+    const int D = c->D, L = c->L, Pl = c->Pl, Kl = c->Kl, Hdl = c->Hdl, Vl = c->Vl, r = tp.rank;
+    const int P = c->H * 128, K = c->KVH * 128;
+
+    auto fail = [&]() -> QwenCudaCtx* {
+        qwen_cuda_destroy(c);
+        return nullptr;
+    };
+
+    // ---- weights -> SG layout ------------------------------------------------
+    c->w_qkv_stride = qw_row_bytes(D) * (size_t) (Pl + 2 * Kl);
+    c->w_o_stride = qw_row_bytes(Pl) * (size_t) D;
+    c->w_13_stride = qw_row_bytes(D) * (size_t) (2 * Hdl);
+    c->w_2_stride = qw_row_bytes(Hdl) * (size_t) D;
+    const size_t cls_bytes = qw_row_bytes(D) * (size_t) Vl, emb_bytes = qw_row_bytes(D) * (size_t) c->V;
+    const bool emb_alias = m->shared_classifier && tp.size == 1;
+    if (dev_alloc(&c->w_qkv, c->w_qkv_stride * L, false) || dev_alloc(&c->w_o, c->w_o_stride * L, false)
+        || dev_alloc(&c->w_13, c->w_13_stride * L, false) || dev_alloc(&c->w_2, c->w_2_stride * L, false)
+        || dev_alloc(&c->w_cls, cls_bytes, false))
+        return fail();
+    if (emb_alias) {
+        c->w_emb = c->w_cls;
+    } else if (dev_alloc(&c->w_emb, emb_bytes, false)) {
+        return fail();
+    }
+    c->bytes_weights = (c->w_qkv_stride + c->w_o_stride + c->w_13_stride + c->w_2_stride) * L + cls_bytes
+                       + (emb_alias ? 0 : emb_bytes);
+    {
+        Stage st;
+        cudaStream_t s = c->stream;
+        for (int l = 0; l < L; ++l) {
+            uint8_t* qkv = c->w_qkv + l * c->w_qkv_stride;
+            if (put(st, m->wq[l], D, r * Pl, Pl, 0, D, qkv, 0, 1, s) || put(st, m->wk[l], D, r * Kl, Kl, 0, D, qkv, Pl, 1, s)
+                || put(st, m->wv[l], D, r * Kl, Kl, 0, D, qkv, Pl + Kl, 1, s)
+                || put(st, m->wo[l], P, 0, D, r * Pl, Pl, c->w_o + l * c->w_o_stride, 0, 1, s)
+                || put(st, m->w1[l], D, r * Hdl, Hdl, 0, D, c->w_13 + l * c->w_13_stride, 0, 2, s)
+                || put(st, m->w3[l], D, r * Hdl, Hdl, 0, D, c->w_13 + l * c->w_13_stride, 1, 2, s)
+                || put(st, m->w2[l], c->Hd, 0, D, r * Hdl, Hdl, c->w_2 + l * c->w_2_stride, 0, 1, s))
+                return fail();
+        }
+        if (put(st, m->cls, D, r * Vl, Vl, 0, D, c->w_cls, 0, 1, s)) return fail();
+        if (!emb_alias && put(st, m->emb, D, 0, c->V, 0, D, c->w_emb, 0, 1, s)) return fail();
+        if (cudaStreamSynchronize(s) != cudaSuccess) {
+            qw_set_error("qwen_cuda_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail();
+        }
+        (void) K;
+    }
+    if (upload_f32(&c->att_norm, m->att_rms_norm, (size_t) L * D) || upload_f32(&c->ffn_norm, m->ffn_rms_norm, (size_t) L * D)
+        || upload_f32(&c->out_norm, m->out_rms_norm, D) || upload_f32(&c->q_norm, m->q_rms_norm, (size_t) L * 128)
+        || upload_f32(&c->k_norm, m->k_rms_norm, (size_t) L * 128)
+        || upload_f32(&c->rope_cos, m->rope_cos, (size_t) c->S * 64) || upload_f32(&c->rope_sin, m->rope_sin, (size_t) c->S * 64))
+        return fail();
+
+    // ---- KV cache + activations ------------------------------------------------
+    const size_t kv = (size_t) L * c->KVHl * c->S * 128;
+    c->bytes_kv = 2 * kv * sizeof(float);
+    if (dev_alloc(&c->k_cache, kv) || dev_alloc(&c->v_cache, kv)) return fail();
+    const int amax = qw_pad_cols(std::max(D, std::max(Pl, Hdl)));
+    c->att_max_splits = 64;
+    c->argmax_cap = 4096;
+    if (dev_alloc(&c->x, D) || dev_alloc(&c->xb, amax) || dev_alloc(&c->qkv, Pl + 2 * Kl) || dev_alloc(&c->q, Pl)
+        || dev_alloc(&c->att, Pl) || dev_alloc(&c->h, Hdl) || dev_alloc(&c->h13, 2 * Hdl) || dev_alloc(&c->logits, Vl)
+        || dev_alloc(&c->aq, amax) || dev_alloc(&c->as, amax / 64) || dev_alloc(&c->token_dev, 1)
+        || dev_alloc(&c->argmax_out, c->argmax_cap) || dev_alloc(&c->att_m, (size_t) c->Hl * c->att_max_splits)
+        || dev_alloc(&c->att_l, (size_t) c->Hl * c->att_max_splits)
+        || dev_alloc(&c->att_acc, (size_t) c->Hl * c->att_max_splits * 128) || dev_alloc(&c->bar_counter, 8))
+        return fail();
+    // error flag lives in mapped pinned memory: the kernel writes it only on a barrier
+    // timeout, the host reads it for free after every synchronise
+    if (cudaHostAlloc((void**) &c->err_flag, 64, cudaHostAllocMapped) != cudaSuccess) {
+        qw_set_error("qwen_cuda_create: pinned error flag allocation failed");
+        return fail();
+    }
+    *c->err_flag = 0;
+    if (cudaMallocHost((void**) &c->logits_pinned, (size_t) Vl * sizeof(float)) != cudaSuccess) {
+        qw_set_error("qwen_cuda_create: pinned logits buffer allocation failed");
+        return fail();
+    }
+    if (qw_mega_init(c)) return fail();
+    return c;
+}
+
+extern "C" void qwen_cuda_destroy(QwenCudaCtx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->w_emb != c->w_cls) cudaFree(c->w_emb);
+    void* bufs[] = {c->w_qkv, c->w_o, c->w_13, c->w_2, c->w_cls, c->att_norm, c->ffn_norm, c->out_norm, c->q_norm,
+                    c->k_norm, c->rope_cos, c->rope_sin, c->k_cache, c->v_cache, c->x, c->xb, c->qkv, c->q, c->att,
+                    c->h, c->h13, c->logits, c->aq, c->as, c->token_dev, c->argmax_out, c->att_m, c->att_l,
+                    c->att_acc, c->bar_counter};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (c->logits_pinned) cudaFreeHost(c->logits_pinned);
+    if (c->err_flag) cudaFreeHost(c->err_flag);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" void* qwen_cuda_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) {
+        qw_set_error("pinned host allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    memset(p, 0, bytes);
+    return p;
+}
+extern "C" void qwen_cuda_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int qwen_cuda_set_path(QwenCudaCtx* c, int path) {
+    if (!c || path < 0 || path > 1) return -2;
+    c->path = path;
+    return 0;
+}
+
+static int step(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
+    if (pos < 0 || pos >= c->S) {
+        qw_set_error("forward: pos %d outside [0, %d)", pos, c->S);
+        return -2;
+    }
+    if (!token_dev && (token < 0 || token >= c->V)) {
+        qw_set_error("forward: token %d outside [0, %d)", token, c->V);
+        return -2;
+    }
+    return c->path == 1 ? qw_decode_ops(c, token, token_dev, pos) : qw_decode_mega(c, token, token_dev, pos);
+}
+
+static int qw_check_flag(QwenCudaCtx* c) {
+    const int flag = *(volatile int*) c->err_flag;
+    if (flag) {
+        qw_set_error("decode kernel reported error %d (grid barrier timeout)", flag);
+        *c->err_flag = 0;
+        return -3;
+    }
+    return 0;
+}
+
+extern "C" int qwen_cuda_forward_async(QwenCudaCtx* c, int token, int pos) {
+    if (!c) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    return step(c, token, nullptr, pos);
+}
+
+extern "C" int qwen_cuda_sync(QwenCudaCtx* c) {
+    if (!c) return -2;
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    return qw_check_flag(c);
+}
+
+extern "C" int qwen_cuda_logits_to_host(QwenCudaCtx* c, float* logits_host) {
+    if (!c || !logits_host) return -2;
+    // each rank owns vocab rows [rank*Vl, (rank+1)*Vl) (classifier is column-parallel over V)
+    QW_CUDA(cudaMemcpyAsync(logits_host + (size_t) c->tp_rank * c->Vl, c->logits, (size_t) c->Vl * sizeof(float),
+                            cudaMemcpyDeviceToHost, c->stream));
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    return qw_check_flag(c);
+}
+
+extern "C" int qwen_cuda_forward(QwenCudaCtx* c, int token, int pos, float* logits_host) {
+    if (!c) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    if (int rc = step(c, token, nullptr, pos)) return rc;
+    return qwen_cuda_logits_to_host(c, logits_host);
+}
+
+extern "C" int qwen_cuda_decode_greedy(QwenCudaCtx* c, int first_token, int pos0, int n, int* out_tokens_host) {
+    if (!c || n < 0 || n > c->argmax_cap || c->tp_size != 1) {
+        qw_set_error("decode_greedy: bad arguments (n %d, cap %d, tp %d)", n, c ? c->argmax_cap : 0, c ? c->tp_size : 0);
+        return -2;
+    }
+    QW_CUDA(cudaSetDevice(c->device));
+    QW_CUDA(cudaMemcpyAsync(c->token_dev, &first_token, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < n; ++i) {
+        if (int rc = step(c, 0, c->token_dev, pos0 + i)) return rc;
+        launch_argmax(c->logits, c->Vl, c->argmax_out + i, c->token_dev, c->stream);
+    }
+    QW_CUDA(cudaMemcpyAsync(out_tokens_host, c->argmax_out, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return qwen_cuda_sync(c);
+}
+
+extern "C" int qwen_cuda_time_decode(QwenCudaCtx* c, int token, int pos0, int steps, int warmup, float* ms_total,
+                                     int* launches) {
+    if (!c || steps <= 0 || warmup < 0) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    int pos = pos0;
+    for (int i = 0; i < warmup; ++i)
+        if (int rc = step(c, token, nullptr, pos++)) return rc;
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    QW_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < steps; ++i)
+        if (int rc = step(c, token, nullptr, pos++)) return rc;
+    QW_CUDA(cudaEventRecord(c->ev1, c->stream));
+    if (int rc = qwen_cuda_sync(c)) return rc;
+    QW_CUDA(cudaEventElapsedTime(ms_total, c->ev0, c->ev1));
+    if (launches) *launches = steps * (c->path == 1 ? qw_decode_ops_launches(c) : qw_decode_mega_launches(c));
+    return 0;
+}
+
+// ---- KV cache access: host side is the reference's [npos][KVH*128] per layer ----
+static int kv_copy(QwenCudaCtx* c, int layer, int pos0, int npos, float* k_host, float* v_host, bool to_device) {
+    if (!c || layer < 0 || layer >= c->L || pos0 < 0 || npos < 0 || pos0 + npos > c->S) {
+        qw_set_error("kv access out of range (layer %d pos %d+%d)", layer, pos0, npos);
+        return -2;
+    }
+    QW_CUDA(cudaSetDevice(c->device));
+    const size_t hpitch = (size_t) c->KVH * 128 * sizeof(float);
+    for (int h = 0; h < c->KVHl; ++h) {
+        const size_t doff = (((size_t) layer * c->KVHl + h) * c->S + pos0) * 128;
+        const size_t hoff = (size_t) (c->tp_rank * c->KVHl + h) * 128;
+        if (to_device) {
+            QW_CUDA(cudaMemcpy2DAsync(c->k_cache + doff, 512, k_host + hoff, hpitch, 512, npos, cudaMemcpyHostToDevice, c->stream));
+            QW_CUDA(cudaMemcpy2DAsync(c->v_cache + doff, 512, v_host + hoff, hpitch, 512, npos, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            QW_CUDA(cudaMemcpy2DAsync(k_host + hoff, hpitch, c->k_cache + doff, 512, 512, npos, cudaMemcpyDeviceToHost, c->stream));
+            QW_CUDA(cudaMemcpy2DAsync(v_host + hoff, hpitch, c->v_cache + doff, 512, 512, npos, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int qwen_cuda_kv_write(QwenCudaCtx* c, int layer, int pos0, int npos, const float* k, const float* v) {
+    return kv_copy(c, layer, pos0, npos, const_cast<float*>(k), const_cast<float*>(v), true);
+}
+extern "C" int qwen_cuda_kv_read(QwenCudaCtx* c, int layer, int pos0, int npos, float* k, float* v) {
+    return kv_copy(c, layer, pos0, npos, k, v, false);
+}
+
+extern "C" int qwen_cuda_debug_read(QwenCudaCtx* c, const char* what, void* host, size_t max_bytes) {
+    if (!c || !what || !host) return -2;
+    const void* src = nullptr;
+    size_t bytes = 0, elems = 0;
+    if (!strcmp(what, "x")) { src = c->x; elems = c->D; bytes = elems * 4; }
+    else if (!strcmp(what, "xb")) { src = c->xb; elems = c->D; bytes = elems * 4; }
+    else if (!strcmp(what, "q")) { src = c->q; elems = c->Pl; bytes = elems * 4; }
+    else if (!strcmp(what, "qkv")) { src = c->qkv; elems = c->Pl + 2 * c->Kl; bytes = elems * 4; }
+    else if (!strcmp(what, "att")) { src = c->att; elems = c->Pl; bytes = elems * 4; }
+    else if (!strcmp(what, "h")) { src = c->h; elems = c->Hdl; bytes = elems * 4; }
+    else if (!strcmp(what, "logits")) { src = c->logits; elems = c->Vl; bytes = elems * 4; }
+    else if (!strcmp(what, "aq")) { src = c->aq; elems = qw_pad_cols(std::max(c->D, std::max(c->Pl, c->Hdl))); bytes = elems; }
+    else if (!strcmp(what, "as")) { src = c->as; elems = qw_pad_cols(std::max(c->D, std::max(c->Pl, c->Hdl))) / 64; bytes = elems * 4; }
+    else {
+        qw_set_error("debug_read: unknown buffer '%s'", what);
+        return -2;
+    }
+    if (bytes > max_bytes) bytes = max_bytes;
+    QW_CUDA(cudaSetDevice(c->device));
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    QW_CUDA(cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost));
+    return (int) elems;
+}
+
+extern "C" int qwen_cuda_attention(QwenCudaCtx* c, int layer, int pos, const float* q_host, float* out_host) {
+    if (!c || layer < 0 || layer >= c->L || pos < 0 || pos >= c->S) {
+        qw_set_error("attention: layer/pos out of range");
+        return -2;
+    }
+    QW_CUDA(cudaSetDevice(c->device));
+    const size_t off = (size_t) c->tp_rank * c->Pl;
+    QW_CUDA(cudaMemcpyAsync(c->q, q_host + off, (size_t) c->Pl * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = qw_attention_device(c, layer, pos, c->q, c->att)) return rc;
+    QW_CUDA(cudaGetLastError());
+    QW_CUDA(cudaMemcpyAsync(out_host + off, c->att, (size_t) c->Pl * 4, cudaMemcpyDeviceToHost, c->stream));
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
