@@ -113,6 +113,8 @@ int qwen_cuda_kv_read(QwenCudaCtx* ctx, int layer, int pos0, int npos, float* k_
 /* Read back a device activation by name ("x", "q", "att", "h", "aq", "as") for layer-by-layer
  * parity tests. Returns the number of elements copied or a negative code. */
 int qwen_cuda_debug_read(QwenCudaCtx* ctx, const char* what, void* host, size_t max_bytes);
+/* Debug: run only the first n layers of the step (then final norm + classifier); -1 = all. */
+int qwen_cuda_debug_set_layers(QwenCudaCtx* ctx, int n);
 
 /* ---- single ops, host in / host out (context-free) ---------------------------
  * Each stands behind the same-named function of include/forward.h / q8.h. */

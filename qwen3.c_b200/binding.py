@@ -102,6 +102,7 @@ class QwenLib:
         L.qwen_cuda_set_path.argtypes = [C.c_void_p, C.c_int]
         L.qwen_cuda_kv_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_kv_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
+        L.qwen_cuda_debug_set_layers.argtypes = [C.c_void_p, C.c_int]
         L.qwen_cuda_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
         L.qwen_cuda_matmul_group_dots.argtypes = [c_int32_p, c_int8_p, c_int8_p, C.c_int, C.c_int, C.c_int]
         L.qwen_cuda_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p]
@@ -196,6 +197,9 @@ class B200Model:
 
     def set_path(self, path: int):
         self.ql._ok(self.ql.lib.qwen_cuda_set_path(self.ctx, path), "set_path")
+
+    def set_layers(self, n: int):
+        self.ql._ok(self.ql.lib.qwen_cuda_debug_set_layers(self.ctx, n), "set_layers")
 
     def decode_greedy(self, first_token: int, pos0: int, n: int) -> np.ndarray:
         out = np.zeros(n, np.int32)

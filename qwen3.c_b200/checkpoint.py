@@ -84,6 +84,7 @@ SHAPES = {
     "tiny": Shape("tiny", 256, 768, 2, 4, 2, 512, seq_len=256),
     "tiny-untied": Shape("tiny-untied", 256, 512, 3, 8, 2, 384, seq_len=192, shared_classifier=0),
     "small": Shape("small", 512, 1536, 4, 8, 4, 2048, seq_len=1024),
+    "0.6b-l1": Shape("0.6b-l1", 1024, 3072, 1, 16, 8, 4096, seq_len=256),
     "0.6b": Shape("0.6b", 1024, 3072, 28, 16, 8, 151936),
     "1.7b": Shape("1.7b", 2048, 6144, 28, 16, 8, 151936),
     "4b": Shape("4b", 2560, 9728, 36, 32, 8, 151936),
@@ -122,14 +123,25 @@ def _q8_fast(rng: np.random.Generator, numel: int, group: int, sigma: float):
 
 
 def write_checkpoint(path: str, shape: Shape, seed: int = 1234, mode: str = "gauss",
-                     sigma: float = 0.02, emb_sigma: float | None = None) -> str:
-    """Write a random-init checkpoint; returns `path`. Deterministic in (shape, seed, mode)."""
+                     sigma: float = 0.02, emb_sigma: float | None = None, rho: float = 0.03) -> str:
+    """Write a random-init checkpoint; returns `path`. Deterministic in (shape, seed, mode, rho).
+
+    Conditioning (SURVEY.md H7 and DESIGN.md "synthetic checkpoints"): a random-init residual
+    network whose branches are as large as its residual stream doubles any perturbation per
+    block, so one flipped int8 activation code (which the reference's own -O2 and -Ofast builds
+    already disagree on) grows to O(0.1) logit differences after 28+ layers. Real checkpoints
+    are not like that: branch outputs are small against the stream. The generator therefore
+    sizes the output projections (wo, w2) so each branch adds about `rho` x the stream's rms,
+    and the embedding so logits have std ~6 (greedy tokens well separated)."""
     rng = np.random.default_rng(seed)
     gen = _q8_gauss if mode == "gauss" else _q8_fast
     D, P, K, Hd, L, V, G, hd = (shape.dim, shape.proj_dim, shape.kv_dim, shape.hidden_dim, shape.n_layers,
                                 shape.vocab_size, shape.group_size, shape.head_dim)
-    # embedding / classifier spread chosen so logits have std ~2 (greedy tokens well separated, SURVEY H7)
-    emb_sigma = (2.0 / float(np.sqrt(D))) if emb_sigma is None else emb_sigma
+    emb_sigma = (6.0 / float(np.sqrt(D))) if emb_sigma is None else emb_sigma
+    # branch gains: attention output ~ rms(v) ~ sigma*sqrt(D); swiglu output rms ~ 0.3*(sigma*sqrt(D))
+    v_rms = sigma * float(np.sqrt(D))
+    wo_sigma = rho * emb_sigma / (float(np.sqrt(P)) * v_rms)
+    w2_sigma = rho * emb_sigma / (float(np.sqrt(Hd)) * 0.3 * v_rms)
     tmp = path + ".part"
     with open(tmp, "wb") as f:
         f.write(struct.pack("<12i", MAGIC, VERSION, D, Hd, L, shape.n_heads, shape.n_kv_heads, V,
@@ -151,9 +163,10 @@ def write_checkpoint(path: str, shape: Shape, seed: int = 1234, mode: str = "gau
             f.write(s.tobytes())
 
         q8(V * D, emb_sigma)
-        for numel in (D * P, D * K, D * K, P * D, D * Hd, Hd * D, D * Hd):
+        for numel, sg in ((D * P, sigma), (D * K, sigma), (D * K, sigma), (P * D, wo_sigma), (D * Hd, sigma),
+                          (Hd * D, w2_sigma), (D * Hd, sigma)):
             for _ in range(L):
-                q8(numel, sigma)
+                q8(numel, sg)
         if not shape.shared_classifier:
             q8(V * D, emb_sigma)
     os.replace(tmp, path)

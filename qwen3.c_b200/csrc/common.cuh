@@ -156,6 +156,8 @@ struct QwenCudaCtx {
     unsigned long long bar_epoch;
     int* err_flag;
 
+    void* mega;       // persistent-kernel state (decode_mega.cu)
+    int layers_run;   // debug: run only the first n layers (-1 = all)
     float* logits_pinned; // optional pinned bounce buffer
     size_t bytes_weights, bytes_kv;
 };
@@ -172,4 +174,5 @@ void launch_repack(const int8_t* src_q, const float* src_s, int src_n, int col0,
 int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos);
 int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos);
 int qw_mega_init(QwenCudaCtx* c);
+void qw_mega_free(QwenCudaCtx* c);
 void launch_argmax(const float* v, int n, int* out, int* also, cudaStream_t st);

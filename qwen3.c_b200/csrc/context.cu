@@ -2,6 +2,7 @@
 // forward entry points of include/qwen_cuda.h. Stands behind model_create /
 // model_free / forward (reference: src/model.c:162-282, 321-406, 491-500;
 // src/forward.c:225-350).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -59,6 +60,7 @@ int put(Stage& st, const QwenCudaQ8& t, int src_n, int row0, int rows, int col0,
     QW_CUDA(cudaMemcpyAsync(st.s, t.s + (size_t) row0 * src_n / 64, codes / 64 * 4, cudaMemcpyHostToDevice, stream));
     launch_repack(st.q, st.s, src_n, col0, n, rows, dst, dst_row0, dst_row_step, stream);
     QW_CUDA(cudaGetLastError());
+    if (getenv("QWEN_CUDA_SYNC_UPLOAD")) QW_CUDA(cudaStreamSynchronize(stream));
     // the staging buffers are reused by the next tensor; pageable-source copies are
     // already synchronous with respect to the host buffer, the kernel is stream ordered
     return 0;
@@ -92,6 +94,7 @@ extern "C" QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* m, int device,
     QwenCudaCtx* c = new QwenCudaCtx();
     memset(c, 0, sizeof *c);
     c->device = device;
+    c->layers_run = -1;
     cudaDeviceProp prop;
     QW_CUDA_NULL(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
@@ -189,6 +192,12 @@ extern "C" QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* m, int device,
         return fail();
     }
     if (qw_mega_init(c)) return fail();
+    // dev_alloc's memsets run on the legacy default stream, which does NOT order against our
+    // non-blocking stream: without this a late memset can zero buffers the first step already wrote
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        qw_set_error("qwen_cuda_create: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail();
+    }
     return c;
 }
 
@@ -196,6 +205,7 @@ extern "C" void qwen_cuda_destroy(QwenCudaCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    qw_mega_free(c);
     if (c->w_emb != c->w_cls) cudaFree(c->w_emb);
     void* bufs[] = {c->w_qkv, c->w_o, c->w_13, c->w_2, c->w_cls, c->att_norm, c->ffn_norm, c->out_norm, c->q_norm,
                     c->k_norm, c->rope_cos, c->rope_sin, c->k_cache, c->v_cache, c->x, c->xb, c->qkv, c->q, c->att,
@@ -224,8 +234,18 @@ extern "C" void qwen_cuda_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+extern "C" int qwen_cuda_debug_set_layers(QwenCudaCtx* c, int n) {
+    if (!c) return -2;
+    c->layers_run = n;
+    return 0;
+}
+
 extern "C" int qwen_cuda_set_path(QwenCudaCtx* c, int path) {
     if (!c || path < 0 || path > 1) return -2;
+    if (path == 0 && c->tp_size != 1) {
+        qw_set_error("persistent kernel path is single-GPU only");
+        return -2;
+    }
     c->path = path;
     return 0;
 }
@@ -247,6 +267,8 @@ static int qw_check_flag(QwenCudaCtx* c) {
     if (flag) {
         qw_set_error("decode kernel reported error %d (grid barrier timeout)", flag);
         *c->err_flag = 0;
+        cudaMemset(c->bar_counter, 0, 8); // the grid-barrier count is meaningless after an abort
+        c->bar_epoch = 0;
         return -3;
     }
     return 0;

@@ -180,7 +180,8 @@ int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         return -2;
     }
     k_embed<<<(D + 255) / 256, 256, 0, st>>>(c->x, c->w_emb, token, token_dev, D);
-    for (int l = 0; l < c->L; ++l) {
+    const int layers = (c->layers_run >= 0 && c->layers_run <= c->L) ? c->layers_run : c->L;
+    for (int l = 0; l < layers; ++l) {
         const size_t loff = (size_t) l * c->KVHl * c->S * 128;
         launch_rmsnorm(c->xb, c->x, c->att_norm + (size_t) l * D, D, st);
         quantize_padded(c, c->xb, D);

@@ -257,6 +257,8 @@ k_gemv_sg(const uint8_t* __restrict__ w, const int8_t* __restrict__ xq, const fl
     const int lane = threadIdx.x & 31;
     const int l16 = lane & 15, half = lane >> 4;
     const int grp = l16 >> 2;
+    // the two half-warps run different trip counts when sgpr is odd: shuffle within the half only
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
     const int warps_per_block = blockDim.x >> 5;
     const int n_groups = n / 64;
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
@@ -268,14 +270,15 @@ k_gemv_sg(const uint8_t* __restrict__ w, const int8_t* __restrict__ xq, const fl
             const int4 wv = __ldg(reinterpret_cast<const int4*>(rec) + l16);
             const int4 xv = reinterpret_cast<const int4*>(sxq + sg * 256)[l16];
             int dot = dot16(wv, xv);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(hmask, dot, 1);
+            dot += __shfl_xor_sync(hmask, dot, 2);
             if ((l16 & 3) == 0) {
                 const float wsc = __ldg(reinterpret_cast<const float*>(rec + 256) + grp);
                 acc = __fadd_rn(acc, q8_term(dot, wsc, sxs[sg * 4 + grp]));
                 if (dots && sg * 4 + grp < n_groups) dots[(size_t) row * n_groups + sg * 4 + grp] = dot;
             }
         }
+        __syncwarp();
         // leaders are lanes 0,4,...,28; everyone else holds 0
         acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
         acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
