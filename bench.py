@@ -1,0 +1,232 @@
+#!/usr/bin/env python
+"""bench.py -- decode throughput of the qwen3.c forward hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one forward() = one decoded token. Workloads (BASELINE.json configs):
+    4b-decode-ctx4096   Qwen3-4B-shape Q8_0, decode at context 4096, 1 GPU   (headline, default at N=1)
+    8b-decode-ctx4096   R1-0528-Qwen3-8B-shape Q8_0, decode at context 4096 (default at N>1)
+    1.7b / 0.6b ...     smaller shapes for quick runs
+Weights are random-init Q8_0 checkpoints written in the reference's .bin format (no network);
+the KV cache is the zero-filled cache the reference also starts from (model.c:360-361): the same
+bytes are read whatever their values.
+
+Prints ONE JSON line (see the task contract): `value` = device-timed tok/s with everything resident
+in HBM; `e2e` = the same steps through the reference-facing C ABI forward(Model*, token, pos) with
+the logits copied back to pinned host memory every step (what the unchanged CLI would see);
+`roofline` = algorithmic bytes/token / device time vs the measured HBM peak;
+`cpu_baseline` = the reference's own -Ofast/OpenMP build timed on this box's host cores on a
+bounded sample. `--impl reference` prints the reference arm's line for the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+CKPT_DIR = os.environ.get("QWEN3_B200_CKPT_DIR", "/tmp/qwen3_b200_ckpt")
+WORKLOADS = {
+    "4b-decode-ctx4096": ("4b", 4096),
+    "8b-decode-ctx4096": ("8b", 4096),
+    "1.7b-decode-ctx512": ("1.7b", 512),
+    "0.6b-decode-ctx128": ("0.6b", 128),
+    "small-decode-ctx128": ("small", 128),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 7 for n, v in zip(names, s[3:7]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ensure_ckpt(pkg, shape_name):
+    t = time.time()
+    path = pkg.checkpoint.ensure_checkpoint(CKPT_DIR, shape_name, seed=1234, mode="fast")
+    log(f"[bench] checkpoint {path} ready in {time.time() - t:.1f}s ({os.path.getsize(path) / 2**30:.2f} GiB)")
+    return path
+
+
+def cpu_reference_run(path, seq_len, pos0, steps, warmup, budget_s=150.0):
+    """Times the reference's own forward() (oracle/_ref, -Ofast -fopenmp) on the host cores.
+    Returns dict(value tok/s, cores, kind, sample, ms_per_step, steps). Bounded by `budget_s`."""
+    from oracle import binding as ob
+    cores = os.cpu_count() or 1
+    kind = "reference"
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    if ob.RefLib.available("fast"):
+        ref = ob.RefLib("fast")
+        t = time.time()
+        m = ref.open(path, seq_len)
+        log(f"[bench] reference model_create {time.time() - t:.1f}s ({os.path.basename(ref.path)}, {cores} threads)")
+        fwd = lambda tok, pos: ref.lib.forward(m, tok, pos)  # noqa: E731
+        close = lambda: ref.close(m)  # noqa: E731
+    else:  # the oracle port always exists
+        kind = "port"
+        cores = 1
+        orc = ob.Oracle()
+        om = orc.open(path, seq_len)
+        fwd = lambda tok, pos: orc.lib.orc_forward(om.h, tok, pos)  # noqa: E731
+        close = om.close
+    t0 = time.time()
+    fwd(7, pos0)
+    first = time.time() - t0
+    w = max(0, min(warmup, int(0.2 * budget_s / max(first, 1e-3)) - 1))
+    for i in range(w):
+        fwd(7, pos0 + 1 + i)
+    k = max(1, min(steps, int(0.7 * budget_s / max(first, 1e-3))))
+    t1 = time.time()
+    for i in range(k):
+        fwd(7, pos0 + 1 + w + i)
+    dt = time.time() - t1
+    close()
+    return {"value": k / dt, "unit": "tok/s", "cores": cores, "kind": kind, "ms_per_step": 1e3 * dt / k, "steps": k,
+            "sample": f"{k} forward() calls at pos {pos0 + 1 + w}.. after {w + 1} warm-up calls, same .bin, "
+                      f"{ob.cpu_model()}, OMP_NUM_THREADS={cores}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="mega", choices=["mega", "ops"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(args.gpus, world)
+    workload = args.workload or ("4b-decode-ctx4096" if n_gpus == 1 else "8b-decode-ctx4096")
+    shape_name, ctx = WORKLOADS[workload]
+    K, W = args.steps, max(args.warmup, 3)
+    pkg = entry._pkg()
+    shape = pkg.checkpoint.SHAPES[shape_name]
+    seq_len = ctx + W + K + 8
+    pos0 = ctx
+    base = {"metric": "decode_tokens_per_s", "unit": "tok/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": workload, "shape": shape_name, "context": ctx, "quant": "Q8_0 (int8 + fp32 scale per 64)",
+                       "kv_cache": "fp32", "weights": "random-init .bin in qwen3.c format (mode=fast, seed 1234)",
+                       "l2": "weights per token (%.2f GB) exceed the 126 MB L2, no flush needed" % (shape.weight_elements() * 17 / 16 / 1e9)}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        path = ensure_ckpt(pkg, shape_name)
+        r = cpu_reference_run(path, seq_len, pos0, K, W)
+        line = dict(base, impl="reference", dtype="int8xint8->int32, fp32", value=r["value"], ms_per_step=r["ms_per_step"],
+                    steps=r["steps"], gpu_launches=0,
+                    cpu_baseline={"value": r["value"], "unit": "tok/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                    e2e={"value": r["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    if n_gpus > 1:
+        import bench_tp  # tensor-parallel arm lives in its own module
+        return bench_tp.run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world)
+
+    ql = pkg.QwenLib()
+    if ql.lib.qwen_cuda_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    path = ensure_ckpt(pkg, shape_name)
+    t = time.time()
+    gm = ql.open(path, seq_len)
+    log(f"[bench] model_create {time.time() - t:.1f}s")
+    gm.set_path(0 if args.path == "mega" else 1)
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    # (1) device-resident: K steps back to back, CUDA events on the launching stream
+    ms, launches = gm.time_decode(7, pos0, K, W)
+    # (2) end to end through forward(): token/pos in, logits copied to pinned host memory every step
+    for i in range(W):
+        gm.forward_nocopy(7, pos0 + i)
+    t0 = time.perf_counter()
+    for i in range(K):
+        ptr = gm.forward_nocopy(7, pos0 + W + i)
+        if not ptr:
+            raise SystemExit("forward failed: " + ql.err())
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ql._ok(ql.lib.qwen_cuda_sync(gm.ctx), "sync")
+
+    tok_s = K / (ms / 1e3)
+    bytes_tok = float(np.mean([shape.decode_bytes(pos0 + W + i) for i in range(K)]))
+    peak, peak_src = measured_peak()
+    achieved = bytes_tok * tok_s / 1e9
+    line = dict(base, value=tok_s, ms_per_step=ms / K, dtype="int8xint8->int32, fp32", clocks=clocks, gpu_launches=launches,
+                e2e={"value": K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": shape.vocab_size * 4},
+                roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                          "traffic": None, "peak_source": peak_src, "bytes_per_token": bytes_tok,
+                          "kernel": "k_decode (persistent, 1 launch/token)" if args.path == "mega" else "per-op kernels",
+                          "frac_of_8TBs_nominal": achieved / 8000.0})
+    line["config"]["path"] = args.path
+    gm.close()
+    if not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(path, seq_len, pos0, 6, 1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "tok/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

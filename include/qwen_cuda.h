@@ -115,6 +115,10 @@ int qwen_cuda_kv_read(QwenCudaCtx* ctx, int layer, int pos0, int npos, float* k_
 int qwen_cuda_debug_read(QwenCudaCtx* ctx, const char* what, void* host, size_t max_bytes);
 /* Debug: run only the first n layers of the step (then final norm + classifier); -1 = all. */
 int qwen_cuda_debug_set_layers(QwenCudaCtx* ctx, int n);
+/* Debug: per-CTA phase timestamps (globaltimer ns) of the persistent kernel, [grid][L+1][16].
+ * enable returns the element count; read returns the grid size. */
+int qwen_cuda_debug_profile_enable(QwenCudaCtx* ctx);
+int qwen_cuda_debug_profile_read(QwenCudaCtx* ctx, unsigned long long* host, size_t max_elems);
 
 /* ---- single ops, host in / host out (context-free) ---------------------------
  * Each stands behind the same-named function of include/forward.h / q8.h. */

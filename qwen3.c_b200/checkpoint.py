@@ -117,7 +117,10 @@ def _q8_gauss(rng: np.random.Generator, numel: int, group: int, sigma: float):
 
 
 def _q8_fast(rng: np.random.Generator, numel: int, group: int, sigma: float):
-    q = rng.integers(-127, 128, size=numel, dtype=np.int8)
+    # 8 codes per 64-bit draw (~8x faster than int8 draws); -128 is folded onto -127 (Q8_0 never emits it)
+    i64 = np.iinfo(np.int64)
+    q = rng.integers(i64.min, i64.max, size=(numel + 7) // 8, dtype=np.int64, endpoint=True).view(np.int8)[:numel]
+    np.maximum(q, -127, out=q)
     s = (np.float32(sigma / 73.3) * rng.uniform(0.5, 1.5, size=numel // group)).astype(np.float32)
     return q, s
 

@@ -234,6 +234,13 @@ extern "C" void qwen_cuda_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int qw_mega_profile_enable(QwenCudaCtx* c);
+int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems);
+extern "C" int qwen_cuda_debug_profile_enable(QwenCudaCtx* c) { return c ? qw_mega_profile_enable(c) : -2; }
+extern "C" int qwen_cuda_debug_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
+    return c ? qw_mega_profile_read(c, host, max_elems) : -2;
+}
+
 extern "C" int qwen_cuda_debug_set_layers(QwenCudaCtx* c, int n) {
     if (!c) return -2;
     c->layers_run = n;

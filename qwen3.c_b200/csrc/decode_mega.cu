@@ -43,6 +43,7 @@ constexpr int kChunk = 28;                  // KV positions per attention unit (
 constexpr int kMaxSlots = 8;
 constexpr int kPartFloats = (kSlotBytes / QW_SG_BYTES) * 4; // group terms of one tile
 constexpr unsigned long long kTimeoutNs = 4000000000ull;
+constexpr int kProfSlots = 16; // per layer: stamps after each phase step (CTA-local, thread 0)
 
 struct MegaParams {
     int D, Hdl, L, Hl, KVHl, Pl, Kl, Vl, S, kv_mul;
@@ -59,6 +60,7 @@ struct MegaParams {
     unsigned long long* bar;
     unsigned long long bar_base;
     int* err;
+    unsigned long long* prof; // optional [CTA][kProfSlots] globaltimer stamps (debug)
     int nslot, off_xq, off_xs, off_scr, off_part, off_misc, off_bar;
 };
 
@@ -67,6 +69,7 @@ struct MegaState {
     float* att_s = nullptr;
     float *part_m = nullptr, *part_l = nullptr, *part_acc = nullptr;
     int grid = 0, nslot = 0;
+    unsigned long long* prof = nullptr;
     size_t smem = 0;
     int off_xq, off_xs, off_scr, off_part, off_misc, off_bar;
 };
@@ -561,35 +564,59 @@ __device__ void combine_attn(const Shared& sh, const MegaParams& p) {
 }
 
 // ---------------------------------------------------------------- consumer main
+__device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
+    if (p.prof && threadIdx.x == 0)
+        p.prof[((size_t) blockIdx.x * (p.L + 1) + l) * kProfSlots + k] = gtime_ns();
+}
+
 __device__ void consumer(const Shared& sh, const MegaParams& p) {
     unsigned it = 0;
     int nbar = 0;
     for (int l = 0; l < p.layers_run; ++l) {
+        stamp(p, l, 0);
         // --- attention block (forward.c:254-298)
         prologue_norm_quant(sh, p, p.att_norm + (size_t) l * p.D, l == 0);
+        stamp(p, l, 1);
         consume_mat<1>(sh, p, ph_qkv(p, l), it, [&](int row, const float* v) { p.qkv[row] = v[0]; });
+        stamp(p, l, 2);
         grid_barrier(sh, p, nbar);
+        stamp(p, l, 3);
         consume_attn(sh, p, l, it);
+        stamp(p, l, 4);
         grid_barrier(sh, p, nbar);
+        stamp(p, l, 5);
         combine_attn(sh, p);
+        stamp(p, l, 6);
         grid_barrier(sh, p, nbar);
+        stamp(p, l, 7);
         prologue_load_codes(sh, p.att_q, p.att_s, p.Pl);
         consume_mat<1>(sh, p, ph_o(p, l), it,
                        [&](int row, const float* v) { p.x[row] = __fadd_rn(__ldcg(p.x + row), v[0]); });
+        stamp(p, l, 8);
         grid_barrier(sh, p, nbar);
+        stamp(p, l, 9);
         // --- feed-forward block (forward.c:303-338)
         prologue_norm_quant(sh, p, p.ffn_norm + (size_t) l * p.D, false);
+        stamp(p, l, 10);
         consume_mat<2>(sh, p, ph_13(p, l), it,
                        [&](int row, const float* v) { p.h[row >> 1] = __fmul_rn(silu_ref(v[0]), v[1]); });
+        stamp(p, l, 11);
         grid_barrier(sh, p, nbar);
+        stamp(p, l, 12);
         prologue_quant_global(sh, p.h, p.Hdl);
+        stamp(p, l, 13);
         consume_mat<1>(sh, p, ph_2(p, l), it,
                        [&](int row, const float* v) { p.x[row] = __fadd_rn(__ldcg(p.x + row), v[0]); });
+        stamp(p, l, 14);
         grid_barrier(sh, p, nbar);
+        stamp(p, l, 15);
     }
+    stamp(p, p.L, 0);
     // --- final norm + classifier (forward.c:344-348)
     prologue_norm_quant(sh, p, p.out_norm, p.layers_run == 0);
+    stamp(p, p.L, 1);
     consume_mat<1>(sh, p, ph_cls(p), it, [&](int row, const float* v) { p.logits[row] = v[0]; });
+    stamp(p, p.L, 2);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ MegaParams p) {
@@ -694,7 +721,7 @@ int qw_mega_init(QwenCudaCtx* c) {
 void qw_mega_free(QwenCudaCtx* c) {
     MegaState* st = state_of(c);
     if (!st) return;
-    void* bufs[] = {st->att_q, st->att_s, st->part_m, st->part_l, st->part_acc};
+    void* bufs[] = {st->att_q, st->att_s, st->part_m, st->part_l, st->part_acc, st->prof};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete st;
@@ -722,6 +749,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.part_m = st->part_m; p.part_l = st->part_l; p.part_acc = st->part_acc;
     p.bar = c->bar_counter; p.bar_base = c->bar_epoch;
     p.err = c->err_flag;
+    p.prof = st->prof;
     p.nslot = st->nslot; p.off_xq = st->off_xq; p.off_xs = st->off_xs; p.off_scr = st->off_scr; p.off_part = st->off_part;
     p.off_misc = st->off_misc; p.off_bar = st->off_bar;
     const int nbar = 6 * p.layers_run;
@@ -732,3 +760,23 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
 }
 
 int qw_decode_mega_launches(const QwenCudaCtx*) { return 1; }
+
+// debug: per-CTA phase timestamps of the NEXT steps; read back with qw_mega_profile_read
+int qw_mega_profile_enable(QwenCudaCtx* c) {
+    MegaState* st = state_of(c);
+    if (!st || !st->grid) return -1;
+    const size_t n = (size_t) st->grid * (c->L + 1) * kProfSlots;
+    if (!st->prof) QW_CUDA(cudaMalloc((void**) &st->prof, n * 8));
+    QW_CUDA(cudaMemset(st->prof, 0, n * 8));
+    QW_CUDA(cudaDeviceSynchronize());
+    return (int) n;
+}
+int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
+    MegaState* st = state_of(c);
+    if (!st || !st->prof) return -1;
+    size_t n = (size_t) st->grid * (c->L + 1) * kProfSlots;
+    if (n > max_elems) n = max_elems;
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    QW_CUDA(cudaMemcpy(host, st->prof, n * 8, cudaMemcpyDeviceToHost));
+    return st->grid;
+}
