@@ -117,6 +117,9 @@ int qwen_cuda_debug_read(QwenCudaCtx* ctx, const char* what, void* host, size_t 
 int qwen_cuda_debug_set_layers(QwenCudaCtx* ctx, int n);
 /* Debug: per-CTA phase timestamps (globaltimer ns) of the persistent kernel, [grid][L+1][16].
  * enable returns the element count; read returns the grid size. */
+/* Debug: per-tile stamps of CTA 0 ([4][8192]: producer issue, consumer wait begin/end, done) for one
+ * consumer warp; host == NULL arms the log, non-NULL reads it back. */
+int qwen_cuda_debug_tile_log(QwenCudaCtx* ctx, int warp, unsigned long long* host);
 int qwen_cuda_debug_profile_enable(QwenCudaCtx* ctx);
 int qwen_cuda_debug_profile_read(QwenCudaCtx* ctx, unsigned long long* host, size_t max_elems);
 

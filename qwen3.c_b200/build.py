@@ -25,6 +25,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 def lib_path() -> str:
     """Path of the built library; raises if it has not been built (no fallback exists)."""
+    override = os.environ.get("QWEN3_LIB_PATH")  # debug: compare kernel variants built side by side
+    if override:
+        return override
     if not os.path.exists(LIB):
         raise FileNotFoundError(
             f"{LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -236,6 +236,8 @@ extern "C" void qwen_cuda_host_free(void* p) {
 
 int qw_mega_profile_enable(QwenCudaCtx* c);
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems);
+int qw_mega_tlog(QwenCudaCtx* c, int warp, unsigned long long* host);
+extern "C" int qwen_cuda_debug_tile_log(QwenCudaCtx* c, int warp, unsigned long long* host) { return c ? qw_mega_tlog(c, warp, host) : -2; }
 extern "C" int qwen_cuda_debug_profile_enable(QwenCudaCtx* c) { return c ? qw_mega_profile_enable(c) : -2; }
 extern "C" int qwen_cuda_debug_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
     return c ? qw_mega_profile_read(c, host, max_elems) : -2;

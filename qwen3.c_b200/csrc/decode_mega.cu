@@ -29,9 +29,15 @@
 // instead of hanging the GPU.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
+
+#ifndef QW_GEMV_PRED
+#define QW_GEMV_PRED 0
+#endif
 
 namespace {
 
@@ -41,37 +47,42 @@ constexpr int kThreads = kConsumerThreads + 32;
 constexpr int kSlotBytes = 28672;           // one ring slot: 105 SG records or 2 x 28 KV rows
 constexpr int kChunk = 28;                  // KV positions per attention unit (2*28*512 B = one slot)
 constexpr int kMaxSlots = 8;
-constexpr int kPartFloats = (kSlotBytes / QW_SG_BYTES) * 4; // group terms of one tile
+constexpr int kMaxGrid = 256;
 constexpr unsigned long long kTimeoutNs = 4000000000ull;
+constexpr int kTileLog = 8192;
 constexpr int kProfSlots = 16; // per layer: stamps after each phase step (CTA-local, thread 0)
 
 struct MegaParams {
     int D, Hdl, L, Hl, KVHl, Pl, Kl, Vl, S, kv_mul;
     int pos, token, layers_run;
+    int copy_split; // debug: issue each tile as this many bulk copies
+    int dbg_mode; // 0 normal; 1 consumers skip the GEMV math (ring throughput test); 2 skip attention math too
     const int* token_dev;
     const uint8_t *w_qkv, *w_o, *w_13, *w_2, *w_cls, *w_emb;
     size_t s_qkv, s_o, s_13, s_2;
     const float *att_norm, *ffn_norm, *out_norm, *q_norm, *k_norm, *rope_cos, *rope_sin;
     float *k_cache, *v_cache;
     float *x, *qkv, *att, *h, *logits;
-    int8_t* att_q;
-    float* att_s;
+    uint8_t* att_q; // attention output, quantised, SG layout (row of Pl columns)
     float *part_m, *part_l, *part_acc;
     unsigned long long* bar;
     unsigned long long bar_base;
     int* err;
+    unsigned long long* tlog; // optional [4][kTileLog] per-tile stamps of CTA 0 (debug)
+    int tlog_warp;
     unsigned long long* prof; // optional [CTA][kProfSlots] globaltimer stamps (debug)
-    int nslot, off_xq, off_xs, off_scr, off_part, off_misc, off_bar;
+    int nslot, off_xq, off_scr, off_misc, off_bar;
 };
 
 struct MegaState {
-    int8_t* att_q = nullptr;
-    float* att_s = nullptr;
+    uint8_t* att_q = nullptr;
     float *part_m = nullptr, *part_l = nullptr, *part_acc = nullptr;
-    int grid = 0, nslot = 0;
+    int grid = 0, nslot = 0, dbg_mode = 0, copy_split = 1;
     unsigned long long* prof = nullptr;
+    unsigned long long* tlog = nullptr;
+    int tlog_warp = 0;
     size_t smem = 0;
-    int off_xq, off_xs, off_scr, off_part, off_misc, off_bar;
+    int off_xq, off_scr, off_misc, off_bar;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -113,13 +124,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 struct Shared {
     uint8_t* ring;
-    int8_t* xq;
-    float* xs;
+    uint8_t* xq;   // activation vector in SG layout: [256 codes][4 scales] records
     float* scr;
-    float* part;
     float* misc;
     uint32_t full, empty; // shared-space addresses of the barrier arrays
     volatile int* abort_flag;
@@ -127,37 +139,42 @@ struct Shared {
 
 __device__ __forceinline__ void mbar_wait(const Shared& sh, const MegaParams& p, uint32_t bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = gtime_ns();
-    while (!mbar_try_wait(bar, parity)) {
-        if (*sh.abort_flag) return;
-        if (gtime_ns() - t0 > kTimeoutNs) {
-            *sh.abort_flag = code;
-            *p.err = code;
-            return;
+    unsigned long long t0 = 0;
+    for (unsigned spin = 1;; ++spin) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spin & 255u) == 0) { // look at the clock only now and then: the common case is a short wait
+            if (*sh.abort_flag) return;
+            const unsigned long long now = gtime_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kTimeoutNs) {
+                *sh.abort_flag = code;
+                *p.err = code;
+                return;
+            }
         }
     }
 }
 
-// grid-wide barrier among the consumer threads of every CTA
+// grid-wide barrier among the consumer threads of every CTA: bar.sync makes the CTA's writes
+// happen-before thread 0's release-add; the acquire poll + bar.sync hands the other CTAs'
+// writes to every thread here (readers use ld.cg / ld.acquire, never L1).
 __device__ __forceinline__ void grid_barrier(const Shared& sh, const MegaParams& p, int& nbar) {
-    __threadfence();
     bar_consumers();
     if (threadIdx.x == 0) {
         const unsigned long long target = p.bar_base + (unsigned long long) (nbar + 1) * gridDim.x;
-        __threadfence();
-        atomicAdd(p.bar, 1ull);
-        if (ld_acquire_u64(p.bar) < target) {
-            const unsigned long long t0 = gtime_ns();
-            while (ld_acquire_u64(p.bar) < target) {
-                if (*sh.abort_flag) break;
-                if (gtime_ns() - t0 > kTimeoutNs) {
+        red_release_add_u64(p.bar, 1ull); // release: orders the CTA's writes (seen through bar.sync) before the count
+        unsigned long long t0 = 0;
+        for (unsigned spin = 1; ld_acquire_u64(p.bar) < target; ++spin) {
+            if ((spin & 1023u) == 0) {
+                const unsigned long long now = gtime_ns();
+                if (t0 == 0) t0 = now;
+                if (*sh.abort_flag || now - t0 > kTimeoutNs) {
                     *sh.abort_flag = 100 + nbar;
                     *p.err = 100 + nbar;
                     break;
                 }
             }
         }
-        __threadfence();
     }
     bar_consumers();
     ++nbar;
@@ -175,7 +192,7 @@ __device__ __forceinline__ void cta_rows(const MatPhase& m, int& r0, int& r1) {
 }
 __device__ __forceinline__ int rows_per_tile(const MatPhase& m) {
     int rt = kSlotBytes / (int) qw_row_bytes(m.n);
-    rt -= rt % m.gran;
+    if (rt >= 2) rt &= ~1; // whole 2-row units per tile
     return rt < m.gran ? m.gran : rt;
 }
 __device__ __forceinline__ MatPhase ph_qkv(const MegaParams& p, int l) { return {p.w_qkv + l * p.s_qkv, p.Pl + 2 * p.Kl, p.D, 1}; }
@@ -202,8 +219,12 @@ __device__ void produce_mat(const Shared& sh, const MegaParams& p, const MatPhas
         const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
         mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 1);
         const uint32_t bytes = (uint32_t) (nr * rb);
+        if (p.tlog && blockIdx.x == 0 && it < kTileLog) p.tlog[it] = gtime_ns();
         mbar_expect_tx(sh.full + slot * 8, bytes);
-        bulk_g2s(smem_u32(sh.ring + (size_t) slot * kSlotBytes), m.base + (size_t) r * rb, bytes, sh.full + slot * 8);
+        const uint32_t dst = smem_u32(sh.ring + (size_t) slot * kSlotBytes);
+        const uint8_t* src = m.base + (size_t) r * rb;
+        const uint32_t piece = ((bytes / p.copy_split) + 15u) & ~15u;
+        for (uint32_t o = 0; o < bytes; o += piece) bulk_g2s(dst + o, src + o, min(piece, bytes - o), sh.full + slot * 8);
     }
 }
 
@@ -216,6 +237,7 @@ __device__ void produce_attn(const Shared& sh, const MegaParams& p, int l, unsig
         const int cnt = min(p.pos, p0 + kChunk) - p0; // slot `pos` itself is produced by this step
         const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
         mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 2);
+        if (p.tlog && blockIdx.x == 0 && it < kTileLog) p.tlog[it] = gtime_ns();
         if (cnt > 0) {
             const size_t off = (((size_t) l * p.KVHl + kvh) * p.S + p0) * 128;
             const uint32_t bytes = (uint32_t) cnt * 512u;
@@ -242,81 +264,197 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
 }
 
 // ---------------------------------------------------------------- consumer: GEMV over ring tiles
-// Epi is called by exactly one thread per unit of `gran` rows with the folded values.
-template <int GRAN, class Epi>
-__device__ void consume_mat(const Shared& sh, const MegaParams& p, const MatPhase& m, unsigned& it, Epi epi) {
+// Work unit = 2 consecutive rows, owned by ONE warp (unit u of the CTA's range -> warp u % 16).
+// Lane L owns Q8_0 groups L, L+32, ... of both rows: a group is 64 codes = 4 x LDS.128 of W per
+// row and 4 x LDS.128 of x, shared by the two rows (x sits in shared memory in the same record
+// layout, so one offset serves both). dp4a has ~24 cycles of dependent latency on this part
+// (measured, scripts/ubench), so each lane keeps FOUR independent dp4a chains in flight: two
+// rows x two groups. The 16-byte pieces are read in a lane-rotated order so every quarter-warp
+// hits 8 distinct 16-byte bank groups despite the 64-byte lane stride (0 excess wavefronts in
+// ncu). Per group the exact int32 dot is scaled as ((float) dot * ws) * xs (forward.c:94-96) and
+// added in fp32; lanes are combined by a shuffle tree.
+// No CTA-wide barrier per tile: warps meet only at the ring's mbarriers, so with one unit per
+// tile (n = 9728) different warps work on different ring slots at the same time.
+// KIND 0: out[row] = v      KIND 1: x[row] += v (residual)      KIND 2: h[row/2] = silu(v0) * v1
+template <int KIND>
+__device__ void consume_mat(const Shared& sh, const MegaParams& p, const MatPhase& m, unsigned& it, float* out) {
     int r0, r1;
     cta_rows(m, r0, r1);
     const int rt = rows_per_tile(m);
     const int sgpr = qw_sg_per_row(m.n);
-    const int groups = m.n / 64;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l16 = lane & 15, half = lane >> 4, grp = l16 >> 2;
-    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
-    const int hw = warp * 2 + half;
-    for (int r = r0; r < r1; r += rt, ++it) {
-        const int nr = min(rt, r1 - r);
+    const size_t rb = (size_t) sgpr * QW_SG_BYTES;
+    const int groups = sgpr * 4; // padded groups carry zero codes and zero scales: they add +0
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rot = (lane & 2);
+    const int nrows = r1 - r0;
+    const int upt = (rt + 1) / 2;             // units per tile (rt is 1 only when a row fills the slot)
+    const int rows_pu = rt >= 2 ? 2 : 1;      // rows per unit
+    const int total = (nrows + rows_pu - 1) / rows_pu;
+    for (int t0 = 0; t0 < total; t0 += upt, ++it) {
         const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
+#ifdef QW_TLOG
+        const bool logme = p.tlog && blockIdx.x == 0 && warp == p.tlog_warp && lane == 0 && it < kTileLog;
+#else
+        constexpr bool logme = false;
+#endif
+        if (logme) p.tlog[kTileLog + it] = gtime_ns();
         mbar_wait(sh, p, sh.full + slot * 8, par, 3);
+        if (logme) p.tlog[2 * kTileLog + it] = gtime_ns();
         const uint8_t* tile = sh.ring + (size_t) slot * kSlotBytes;
-        float* part = sh.part + (it & 1) * kPartFloats;
-        const int nsg = nr * sgpr;
-        for (int s = hw; s < nsg; s += 2 * kConsumerWarps) {
-            const int c = s % sgpr;
-            const uint8_t* rec = tile + (size_t) s * QW_SG_BYTES;
-            const int4 wv = *reinterpret_cast<const int4*>(rec + 16 * l16);
-            const int4 xv = *reinterpret_cast<const int4*>(sh.xq + c * 256 + 16 * l16);
-            int dot = dot16(wv, xv);
-            dot += __shfl_xor_sync(hmask, dot, 1);
-            dot += __shfl_xor_sync(hmask, dot, 2);
-            if ((l16 & 3) == 0)
-                part[s * 4 + grp] = q8_term(dot, *reinterpret_cast<const float*>(rec + 256 + 4 * grp), sh.xs[c * 4 + grp]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sh.empty + slot * 8); // slot may be refilled
-        bar_consumers();
-        // fold: one thread per unit, group terms left to right from 0.0f (reference forward.c:86-99)
-        for (int rr = 0; rr < nr; rr += GRAN) {
-            const int g = (r - r0 + rr) / GRAN;
-            if ((g & (kConsumerWarps - 1)) == warp && ((g >> 4) & 31) == lane) {
-                float v[GRAN];
+        const int t1 = p.dbg_mode >= 1 ? t0 : min(t0 + upt, total);
+        int ufirst = (warp - t0) % kConsumerWarps; // first unit >= t0 owned by this warp (u % 15 == warp)
+        if (ufirst < 0) ufirst += kConsumerWarps;
+        for (int u = t0 + ufirst; u < t1; u += kConsumerWarps) {
+            const int lr = (u - t0) * rows_pu;          // first row of the unit inside the tile
+            const int grow = r0 + u * rows_pu;          // its global row
+            const bool two = rows_pu == 2 && grow + 1 < r1;
+            const uint8_t* rowa = tile + (size_t) lr * rb;
+            const uint8_t* rowb = two ? rowa + rb : rowa;
+            float xres = 0.0f;
+            if (KIND == 1 && lane < 2 && (lane == 0 || two)) xres = __ldcg(out + grow + lane); // hide the L2 round trip
+            float acca = 0.0f, accb = 0.0f;
+            for (int G = lane; G < groups; G += 64) {
+                const int G2 = G + 32;
+                const bool has2 = G2 < groups;
+                const int off = (G >> 2) * QW_SG_BYTES + (G & 3) * 64;
+#if QW_GEMV_PRED
+                const int off2 = (G2 >> 2) * QW_SG_BYTES + (G2 & 3) * 64;
+                int da0 = 0, da1 = 0, db0 = 0, db1 = 0;
+                if (has2) {
+#pragma unroll 2
+                    for (int i = 0; i < 4; ++i) {
+                        const int pc = ((i + rot) & 3) * 16;
+                        const int4 x0 = *reinterpret_cast<const int4*>(sh.xq + off + pc);
+                        const int4 x1 = *reinterpret_cast<const int4*>(sh.xq + off2 + pc);
+                        const int4 a0 = *reinterpret_cast<const int4*>(rowa + off + pc);
+                        const int4 a1 = *reinterpret_cast<const int4*>(rowa + off2 + pc);
+                        const int4 b0 = *reinterpret_cast<const int4*>(rowb + off + pc);
+                        const int4 b1 = *reinterpret_cast<const int4*>(rowb + off2 + pc);
+                        da0 = __dp4a(a0.x, x0.x, da0); da1 = __dp4a(a1.x, x1.x, da1); db0 = __dp4a(b0.x, x0.x, db0); db1 = __dp4a(b1.x, x1.x, db1);
+                        da0 = __dp4a(a0.y, x0.y, da0); da1 = __dp4a(a1.y, x1.y, da1); db0 = __dp4a(b0.y, x0.y, db0); db1 = __dp4a(b1.y, x1.y, db1);
+                        da0 = __dp4a(a0.z, x0.z, da0); da1 = __dp4a(a1.z, x1.z, da1); db0 = __dp4a(b0.z, x0.z, db0); db1 = __dp4a(b1.z, x1.z, db1);
+                        da0 = __dp4a(a0.w, x0.w, da0); da1 = __dp4a(a1.w, x1.w, da1); db0 = __dp4a(b0.w, x0.w, db0); db1 = __dp4a(b1.w, x1.w, db1);
+                    }
+                } else { // lanes without a second group issue no loads for it (a partial warp LDS costs fewer wavefronts)
+                    int dc0 = 0, dc1 = 0; // split each row's chain in two to keep four chains in flight
 #pragma unroll
-                for (int k = 0; k < GRAN; ++k) {
-                    const float* t = part + (size_t) (rr + k) * sgpr * 4;
-                    float acc = 0.0f;
-                    for (int j = 0; j < groups; ++j) acc = __fadd_rn(acc, t[j]);
-                    v[k] = acc;
+                    for (int i = 0; i < 4; ++i) {
+                        const int pc = ((i + rot) & 3) * 16;
+                        const int4 x0 = *reinterpret_cast<const int4*>(sh.xq + off + pc);
+                        const int4 a0 = *reinterpret_cast<const int4*>(rowa + off + pc);
+                        const int4 b0 = *reinterpret_cast<const int4*>(rowb + off + pc);
+                        da0 = __dp4a(a0.x, x0.x, da0); dc0 = __dp4a(a0.y, x0.y, dc0); db0 = __dp4a(b0.x, x0.x, db0); dc1 = __dp4a(b0.y, x0.y, dc1);
+                        da0 = __dp4a(a0.z, x0.z, da0); dc0 = __dp4a(a0.w, x0.w, dc0); db0 = __dp4a(b0.z, x0.z, db0); dc1 = __dp4a(b0.w, x0.w, dc1);
+                    }
+                    da0 += dc0;
+                    db0 += dc1;
                 }
-                epi(r + rr, v);
+#else
+                const int off2 = has2 ? (G2 >> 2) * QW_SG_BYTES + (G2 & 3) * 64 : off;
+                int da0 = 0, da1 = 0, db0 = 0, db1 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int pc = ((i + rot) & 3) * 16;
+                    const int4 x0 = *reinterpret_cast<const int4*>(sh.xq + off + pc);
+                    const int4 x1 = *reinterpret_cast<const int4*>(sh.xq + off2 + pc);
+                    const int4 a0 = *reinterpret_cast<const int4*>(rowa + off + pc);
+                    const int4 a1 = *reinterpret_cast<const int4*>(rowa + off2 + pc);
+                    const int4 b0 = *reinterpret_cast<const int4*>(rowb + off + pc);
+                    const int4 b1 = *reinterpret_cast<const int4*>(rowb + off2 + pc);
+                    da0 = __dp4a(a0.x, x0.x, da0); da1 = __dp4a(a1.x, x1.x, da1); db0 = __dp4a(b0.x, x0.x, db0); db1 = __dp4a(b1.x, x1.x, db1);
+                    da0 = __dp4a(a0.y, x0.y, da0); da1 = __dp4a(a1.y, x1.y, da1); db0 = __dp4a(b0.y, x0.y, db0); db1 = __dp4a(b1.y, x1.y, db1);
+                    da0 = __dp4a(a0.z, x0.z, da0); da1 = __dp4a(a1.z, x1.z, da1); db0 = __dp4a(b0.z, x0.z, db0); db1 = __dp4a(b1.z, x1.z, db1);
+                    da0 = __dp4a(a0.w, x0.w, da0); da1 = __dp4a(a1.w, x1.w, da1); db0 = __dp4a(b0.w, x0.w, db0); db1 = __dp4a(b1.w, x1.w, db1);
+                }
+#endif
+                const int so = (G >> 2) * QW_SG_BYTES + 256 + (G & 3) * 4;
+                const float xs0 = *reinterpret_cast<const float*>(sh.xq + so);
+                acca = __fadd_rn(acca, q8_term(da0, *reinterpret_cast<const float*>(rowa + so), xs0));
+                accb = __fadd_rn(accb, q8_term(db0, *reinterpret_cast<const float*>(rowb + so), xs0));
+                if (has2) {
+                    const int so2 = (G2 >> 2) * QW_SG_BYTES + 256 + (G2 & 3) * 4;
+                    const float xs1 = *reinterpret_cast<const float*>(sh.xq + so2);
+                    acca = __fadd_rn(acca, q8_term(da1, *reinterpret_cast<const float*>(rowa + so2), xs1));
+                    accb = __fadd_rn(accb, q8_term(db1, *reinterpret_cast<const float*>(rowb + so2), xs1));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acca = __fadd_rn(acca, __shfl_xor_sync(0xffffffffu, acca, o));
+                accb = __fadd_rn(accb, __shfl_xor_sync(0xffffffffu, accb, o));
+            }
+            if (KIND == 2) {
+                if (lane == 0) out[grow >> 1] = __fmul_rn(silu_ref(acca), accb);
+            } else if (lane < 2 && (lane == 0 || two)) {
+                const float v = lane == 0 ? acca : accb;
+                out[grow + lane] = KIND == 1 ? __fadd_rn(xres, v) : v;
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sh.empty + slot * 8); // this warp is done with the slot
+        if (logme) p.tlog[3 * kTileLog + it] = gtime_ns();
     }
 }
 
 // ---------------------------------------------------------------- consumer: prologues
-// x (fp32, D) -> RMSNorm with weights w -> Q8_0 codes + scales in shared memory.
-// layer0: the residual stream starts as the dequantised embedding row (forward.c:237).
+// store one quantised group (64 codes + scale) into the shared activation vector (SG layout)
+__device__ __forceinline__ void put_group(uint8_t* xq, int g, int lane, float a, float b) {
+    const float scale = q8_scale(warp_max(fmaxf(fabsf(a), fabsf(b))));
+    int8_t* codes = reinterpret_cast<int8_t*>(xq + (g >> 2) * QW_SG_BYTES + (g & 3) * 64);
+    codes[lane] = (int8_t) q8_code(a, scale);
+    codes[lane + 32] = (int8_t) q8_code(b, scale);
+    if (lane == 0) *reinterpret_cast<float*>(xq + (g >> 2) * QW_SG_BYTES + 256 + (g & 3) * 4) = scale;
+}
+__device__ __forceinline__ void zero_group(uint8_t* xq, int g, int lane) {
+    int8_t* codes = reinterpret_cast<int8_t*>(xq + (g >> 2) * QW_SG_BYTES + (g & 3) * 64);
+    codes[lane] = 0;
+    codes[lane + 32] = 0;
+    if (lane == 0) *reinterpret_cast<float*>(xq + (g >> 2) * QW_SG_BYTES + 256 + (g & 3) * 4) = 0.0f;
+}
+
+constexpr int kMaxGroupsPerWarpNorm = 8; // D <= 8192
+
+// x (fp32, D) -> RMSNorm with weights w -> Q8_0 codes + scales in shared memory (forward.c:254-259).
+// Warp w owns groups w, w+16, ...; all its loads are issued up front (one L2 round trip).
+// from_embedding: the residual stream starts as the dequantised embedding row (forward.c:237).
 __device__ void prologue_norm_quant(const Shared& sh, const MegaParams& p, const float* __restrict__ w, bool from_embedding) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D;
-    float* sx = sh.scr;
+    const int groups = D / 64, pad_groups = qw_pad_cols(D) / 64;
+    float va[kMaxGroupsPerWarpNorm], vb[kMaxGroupsPerWarpNorm];
     if (from_embedding) {
         const int tok = p.token_dev ? *p.token_dev : p.token;
         const uint8_t* row = p.w_emb + (size_t) tok * qw_row_bytes(D);
-        for (int i = tid; i < D; i += kConsumerThreads) {
-            const uint8_t* rec = row + (size_t) (i >> 8) * QW_SG_BYTES;
-            const int within = i & 255;
-            const float v = __fmul_rn((float) reinterpret_cast<const int8_t*>(rec)[within],
-                                      reinterpret_cast<const float*>(rec + 256)[within >> 6]);
-            sx[i] = v;
-            if ((i / kConsumerThreads) % gridDim.x == blockIdx.x) p.x[i] = v; // each element stored once chip-wide
+#pragma unroll
+        for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
+            const int g = warp + k * kConsumerWarps;
+            va[k] = vb[k] = 0.0f;
+            if (g < groups) {
+                const uint8_t* rec = row + (size_t) (g >> 2) * QW_SG_BYTES;
+                const float sc = *reinterpret_cast<const float*>(rec + 256 + (g & 3) * 4);
+                const int8_t* codes = reinterpret_cast<const int8_t*>(rec + (g & 3) * 64);
+                va[k] = __fmul_rn((float) codes[lane], sc);
+                vb[k] = __fmul_rn((float) codes[lane + 32], sc);
+                if (blockIdx.x == 0) { // the residual stream lives in global memory; CTA 0 seeds it
+                    p.x[g * 64 + lane] = va[k];
+                    p.x[g * 64 + 32 + lane] = vb[k];
+                }
+            }
         }
     } else {
-        for (int i = tid; i < D; i += kConsumerThreads) sx[i] = __ldcg(p.x + i);
+#pragma unroll
+        for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
+            const int g = warp + k * kConsumerWarps;
+            va[k] = vb[k] = 0.0f;
+            if (g < groups) {
+                va[k] = __ldcg(p.x + g * 64 + lane);
+                vb[k] = __ldcg(p.x + g * 64 + 32 + lane);
+            }
+        }
     }
-    bar_consumers();
     float ss = 0.0f;
-    for (int i = tid; i < D; i += kConsumerThreads) ss = __fadd_rn(ss, __fmul_rn(sx[i], sx[i]));
+#pragma unroll
+    for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) ss = __fadd_rn(ss, __fadd_rn(__fmul_rn(va[k], va[k]), __fmul_rn(vb[k], vb[k])));
     ss = warp_sum(ss);
     if (lane == 0) sh.misc[warp] = ss;
     bar_consumers();
@@ -324,20 +462,15 @@ __device__ void prologue_norm_quant(const Shared& sh, const MegaParams& p, const
 #pragma unroll
     for (int i = 0; i < kConsumerWarps; ++i) tot = __fadd_rn(tot, sh.misc[i]);
     const float r = rms_rscale(tot, D);
-    const int groups = D / 64, pad_groups = qw_pad_cols(D) / 64;
-    for (int g = warp; g < pad_groups; g += kConsumerWarps) {
+#pragma unroll
+    for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
+        const int g = warp + k * kConsumerWarps;
         if (g < groups) {
-            const int i0 = g * 64 + lane, i1 = i0 + 32;
-            const float a = __fmul_rn(__ldg(w + i0), __fmul_rn(r, sx[i0]));
-            const float b = __fmul_rn(__ldg(w + i1), __fmul_rn(r, sx[i1]));
-            const float scale = q8_scale(warp_max(fmaxf(fabsf(a), fabsf(b))));
-            sh.xq[i0] = (int8_t) q8_code(a, scale);
-            sh.xq[i1] = (int8_t) q8_code(b, scale);
-            if (lane == 0) sh.xs[g] = scale;
-        } else {
-            sh.xq[g * 64 + lane] = 0;
-            sh.xq[g * 64 + 32 + lane] = 0;
-            if (lane == 0) sh.xs[g] = 0.0f;
+            const float a = __fmul_rn(__ldg(w + g * 64 + lane), __fmul_rn(r, va[k]));
+            const float b = __fmul_rn(__ldg(w + g * 64 + 32 + lane), __fmul_rn(r, vb[k]));
+            put_group(sh.xq, g, lane, a, b);
+        } else if (g < pad_groups) {
+            zero_group(sh.xq, g, lane);
         }
     }
     bar_consumers();
@@ -347,219 +480,331 @@ __device__ void prologue_norm_quant(const Shared& sh, const MegaParams& p, const
 __device__ void prologue_quant_global(const Shared& sh, const float* src, int n) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int groups = n / 64, pad_groups = qw_pad_cols(n) / 64;
-    for (int g = warp; g < pad_groups; g += kConsumerWarps) {
-        if (g < groups) {
-            const float a = __ldcg(src + g * 64 + lane), b = __ldcg(src + g * 64 + 32 + lane);
-            const float scale = q8_scale(warp_max(fmaxf(fabsf(a), fabsf(b))));
-            sh.xq[g * 64 + lane] = (int8_t) q8_code(a, scale);
-            sh.xq[g * 64 + 32 + lane] = (int8_t) q8_code(b, scale);
-            if (lane == 0) sh.xs[g] = scale;
-        } else {
-            sh.xq[g * 64 + lane] = 0;
-            sh.xq[g * 64 + 32 + lane] = 0;
-            if (lane == 0) sh.xs[g] = 0.0f;
+    constexpr int kBatch = 8;
+    for (int g0 = warp; g0 < pad_groups; g0 += kBatch * kConsumerWarps) {
+        float va[kBatch], vb[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int g = g0 + k * kConsumerWarps;
+            va[k] = vb[k] = 0.0f;
+            if (g < groups) {
+                va[k] = __ldcg(src + g * 64 + lane);
+                vb[k] = __ldcg(src + g * 64 + 32 + lane);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int g = g0 + k * kConsumerWarps;
+            if (g < groups) put_group(sh.xq, g, lane, va[k], vb[k]);
+            else if (g < pad_groups) zero_group(sh.xq, g, lane);
         }
     }
     bar_consumers();
 }
 
-// already-quantised vector (attention output) from global -> shared
-__device__ void prologue_load_codes(const Shared& sh, const int8_t* q, const float* s, int n) {
-    const int tid = threadIdx.x;
-    const int pad = qw_pad_cols(n);
-    for (int i = tid; i < pad / 16; i += kConsumerThreads) {
-        int4 v = make_int4(0, 0, 0, 0);
-        if (i * 16 < n) v = __ldcg(reinterpret_cast<const int4*>(q) + i);
-        reinterpret_cast<int4*>(sh.xq)[i] = v;
-    }
-    for (int i = tid; i < pad / 64; i += kConsumerThreads) sh.xs[i] = i < n / 64 ? __ldcg(s + i) : 0.0f;
+// already-quantised vector (attention output, SG layout in global) -> shared
+__device__ void prologue_load_codes(const Shared& sh, const uint8_t* q, int n) {
+    const int bytes = (int) qw_row_bytes(n);
+    for (int i = threadIdx.x; i < bytes / 16; i += kConsumerThreads)
+        reinterpret_cast<int4*>(sh.xq)[i] = __ldcg(reinterpret_cast<const int4*>(q) + i);
     bar_consumers();
 }
 
 // ---------------------------------------------------------------- consumer: attention
-// scratch layout inside sh.scr (floats): raw[1024] | sq[1024] | ssc[8*28] | so[128]
-__device__ void head_norm_rope(float* dst, const float* raw, const float* g, const MegaParams& p, float r, int i) {
-    // called by 128 threads of one head after raw[] and r are ready; writes dst[i]
+// scratch (floats, inside sh.scr): raw[1280] | sq[1280] | scores[4 groups][8 heads][32]
+constexpr int kScrRaw = 0, kScrQ = 1280, kScrS = 2560;
+constexpr int kScrFloats = kScrS + 4 * 8 * 32;
+
+// RMSNorm weight + RoPE for element i of a 128-wide head (forward.c:267-280, 104-118);
+// cos/sin come from the host-computed table so the angles are the reference's bit for bit.
+__device__ __forceinline__ float head_norm_rope(const float* raw, const float* g, const MegaParams& p, float r, int i) {
     const int j = i & 63;
     const float c = __ldg(p.rope_cos + (size_t) p.pos * 64 + j), s = __ldg(p.rope_sin + (size_t) p.pos * 64 + j);
     const float a = __fmul_rn(__ldg(g + j), __fmul_rn(r, raw[j]));
     const float b = __fmul_rn(__ldg(g + j + 64), __fmul_rn(r, raw[j + 64]));
-    dst[i] = (i < 64) ? __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, s)) : __fadd_rn(__fmul_rn(a, s), __fmul_rn(b, c));
+    return (i < 64) ? __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, s)) : __fadd_rn(__fmul_rn(a, s), __fmul_rn(b, c));
 }
-// sequential sum of squares over 128 values: the reference's order (forward.c:16-19), so the
-// per-head q/k norms are bit-identical to the reference for identical inputs
-__device__ float head_rscale(const float* raw) {
-    float ss = 0.0f;
-    for (int i = 0; i < 128; ++i) ss = __fadd_rn(ss, __fmul_rn(raw[i], raw[i]));
-    return rms_rscale(ss, 128);
+// sum of squares over 128 values by one warp (4 per lane, then the shuffle tree)
+__device__ __forceinline__ float head_rscale_warp(const float* raw, int lane) {
+    const float4 v = *reinterpret_cast<const float4*>(raw + lane * 4);
+    float ss = __fmul_rn(v.x, v.x);
+    ss = __fmaf_rn(v.y, v.y, ss);
+    ss = __fmaf_rn(v.z, v.z, ss);
+    ss = __fmaf_rn(v.w, v.w, ss);
+    return rms_rscale(warp_sum(ss), 128);
 }
 
+// Split-KV attention for the units of this CTA. The 16 consumer warps form 4 groups of 4 warps;
+// each group takes whole 28-position tiles (unit i of a segment -> group i % 4) and runs the three
+// stages of a tile -- scores, online-softmax update, P.V -- synchronised by its OWN named barrier
+// (128 threads), so four tiles are in flight per SM and no CTA-wide barrier sits in the tile loop.
+//   scores : 8 lanes per position (lane covers float4 columns sub, sub+8, sub+16, sub+24 -> every
+//            quarter-warp reads 128 contiguous bytes of K), all KV_MUL heads, 3-step shuffle tree;
+//   softmax: warp w of the group owns heads w, w+4; lane = position;
+//   P.V    : thread = (head, 4 output dims), float4 accumulator in registers.
+// A segment = the CTA's units of one KV head; its query heads (and, if the CTA owns the last
+// chunk, this step's own K/V row: RMSNorm + RoPE, written to the cache for later steps) are
+// prepared once per segment with CTA-wide barriers, and the 4 group states are merged at its end.
+constexpr int kAttnGroups = 4, kAttnGT = 128;
+__device__ __forceinline__ void bar_group(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(kAttnGT) : "memory");
+}
+
+template <int KV_MUL>
 __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsigned& it) {
+    constexpr int NACC = (KV_MUL * 32 + kAttnGT - 1) / kAttnGT; // float4 accumulators per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kv_mul = p.kv_mul;
-    float* raw = sh.scr;
-    float* sq = sh.scr + 1024;
-    float* ssc = sh.scr + 2048;
-    float* s_m = sh.misc + 32;
-    float* s_l = sh.misc + 40;
-    float* s_scale = sh.misc + 48;
-    float* s_r = sh.misc + 56;
+    const int grp = warp >> 2, gw = warp & 3, gt = tid & (kAttnGT - 1);
+    float* raw = sh.scr + kScrRaw;   // [KV_MUL*128 q | 128 k | 128 v] raw projections; reused as flush scratch
+    float* sq = sh.scr + kScrQ;      // [KV_MUL*128] normalised + rotated q, then [128] k, [128] v of this step
+    float* sc = sh.scr + kScrS + grp * (8 * 32); // this group's scores / probabilities [head][32]
+    float* s_r = sh.misc + 16;
+    float* g_m = sh.misc + 64 + grp * 32;  // running max per head
+    float* g_l = g_m + 8;                  // running sum per head
+    float* g_scale = g_m + 16;             // rescale factor of the last update
     int nc, u0, u1;
     attn_units(p, nc, u0, u1);
     const float* gq = p.q_norm + (size_t) l * 128;
     const float* gk = p.k_norm + (size_t) l * 128;
     const float inv = sqrtf(128.0f);
-    float acc[2] = {0.0f, 0.0f};
-    int cur = -1;
-    auto flush = [&](int kvh) {
+    const unsigned it_base = it;
+    float4 acc[NACC];
+
+    // one tile: cnt positions, K rows at Kt, V rows at Vt (shared memory)
+    auto tile = [&](const float* Kt, const float* Vt, int cnt) {
+        // ---- scores (forward.c:156-165)
+        const int sub = gt & 7;
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const int pos = r * 16 + (gt >> 3);
+            const int pc = min(pos, cnt - 1); // idle lanes recompute a valid row: uniform control flow for the shuffles
+            float d[KV_MUL];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int idx = tid + k * kConsumerThreads;
-            if (idx < kv_mul * 128) {
-                const int j = idx >> 7, d = idx & 127, h = kvh * kv_mul + j;
-                const size_t slot = (size_t) h * gridDim.x + blockIdx.x;
-                p.part_acc[slot * 128 + d] = acc[k];
-                if (d == 0) {
-                    p.part_m[slot] = s_m[j];
-                    p.part_l[slot] = s_l[j];
+            for (int j = 0; j < KV_MUL; ++j) d[j] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 kf = *reinterpret_cast<const float4*>(Kt + pc * 128 + (sub + 8 * i) * 4);
+#pragma unroll
+                for (int j = 0; j < KV_MUL; ++j) {
+                    const float4 qf = *reinterpret_cast<const float4*>(sq + j * 128 + (sub + 8 * i) * 4);
+                    d[j] = __fmaf_rn(qf.x, kf.x, d[j]);
+                    d[j] = __fmaf_rn(qf.y, kf.y, d[j]);
+                    d[j] = __fmaf_rn(qf.z, kf.z, d[j]);
+                    d[j] = __fmaf_rn(qf.w, kf.w, d[j]);
                 }
             }
-        }
-    };
-    for (int u = u0; u < u1; ++u, ++it) {
-        const int kvh = u / nc, c = u % nc;
-        const int p0 = c * kChunk;
-        const bool last = (c == nc - 1);
-        const int cnt = min(p.pos + 1, p0 + kChunk) - p0;
-        if (kvh != cur) {
-            if (cur >= 0) flush(cur);
-            bar_consumers();
-            for (int i = tid; i < kv_mul * 128; i += kConsumerThreads) raw[i] = __ldcg(p.qkv + (size_t) kvh * kv_mul * 128 + i);
-            bar_consumers();
-            if (tid < kv_mul) s_r[tid] = head_rscale(raw + tid * 128);
-            bar_consumers();
-            for (int i = tid; i < kv_mul * 128; i += kConsumerThreads)
-                head_norm_rope(sq + (i & ~127), raw + (i & ~127), gq, p, s_r[i >> 7], i & 127);
-            if (tid < kv_mul) {
-                s_m[tid] = -INFINITY;
-                s_l[tid] = 0.0f;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < KV_MUL; ++j) d[j] = __fadd_rn(d[j], __shfl_xor_sync(0xffffffffu, d[j], o));
             }
-            acc[0] = acc[1] = 0.0f;
-            cur = kvh;
-        }
-        const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
-        mbar_wait(sh, p, sh.full + slot * 8, par, 4);
-        float* Kt = reinterpret_cast<float*>(sh.ring + (size_t) slot * kSlotBytes);
-        float* Vt = Kt + kChunk * 128;
-        bar_consumers(); // sq ready; previous unit's PV reads of ssc are done
-        if (last) {
-            // this step's own K/V row: norm + rope K, raw V; into the tile and into the cache
-            const int il = p.pos - p0;
-            const size_t coff = (((size_t) l * p.KVHl + kvh) * p.S + p.pos) * 128;
-            if (tid < 128) raw[tid] = __ldcg(p.qkv + p.Pl + (size_t) kvh * 128 + tid);
-            else if (tid < 256) {
-                const float v = __ldcg(p.qkv + p.Pl + p.Kl + (size_t) kvh * 128 + (tid - 128));
-                Vt[il * 128 + (tid - 128)] = v;
-                p.v_cache[coff + (tid - 128)] = v;
-            }
-            bar_consumers();
-            if (tid == 0) s_r[8] = head_rscale(raw);
-            bar_consumers();
-            if (tid < 128) {
-                head_norm_rope(Kt + il * 128, raw, gk, p, s_r[8], tid);
-                p.k_cache[coff + tid] = Kt[il * 128 + tid];
-            }
-            bar_consumers();
-        }
-        // scores (forward.c:156-165)
-        for (int i = warp; i < cnt; i += kConsumerWarps) {
-            const float4 kv = *reinterpret_cast<const float4*>(Kt + i * 128 + lane * 4);
-            for (int j = 0; j < kv_mul; ++j) {
-                const float4 qv = *reinterpret_cast<const float4*>(sq + j * 128 + lane * 4);
-                float d = __fmul_rn(qv.x, kv.x);
-                d = __fmaf_rn(qv.y, kv.y, d);
-                d = __fmaf_rn(qv.z, kv.z, d);
-                d = __fmaf_rn(qv.w, kv.w, d);
-                d = warp_sum(d);
-                if (lane == 0) ssc[j * kChunk + i] = __fdiv_rn(d, inv);
+            if (sub == 0 && pos < cnt) {
+#pragma unroll
+                for (int j = 0; j < KV_MUL; ++j) sc[j * 32 + pos] = __fdiv_rn(d[j], inv); // score / sqrtf(head_dim)
             }
         }
-        bar_consumers();
-        // online softmax update, one warp per query head
-        if (warp < kv_mul) {
-            const int j = warp;
-            const float s = lane < cnt ? ssc[j * kChunk + lane] : -INFINITY;
-            const float m_old = s_m[j];
+        bar_group(grp);
+        // ---- online softmax update: warp gw owns heads gw, gw+4; lane = position
+        for (int j = gw; j < KV_MUL; j += 4) {
+            const float s = lane < cnt ? sc[j * 32 + lane] : -INFINITY;
+            const float m_old = g_m[j];
             const float m_new = fmaxf(m_old, warp_max(s));
             const float e = lane < cnt ? expf(__fsub_rn(s, m_new)) : 0.0f;
-            if (lane < cnt) ssc[j * kChunk + lane] = e;
+            if (lane < cnt) sc[j * 32 + lane] = e;
             const float lsum = warp_sum(e);
             if (lane == 0) {
-                const float sc = expf(__fsub_rn(m_old, m_new));
-                s_scale[j] = sc;
-                s_l[j] = __fmaf_rn(s_l[j], sc, lsum);
-                s_m[j] = m_new;
+                const float scl = (m_old == -INFINITY) ? 0.0f : expf(__fsub_rn(m_old, m_new));
+                g_scale[j] = scl;
+                g_l[j] = __fmaf_rn(g_l[j], scl, lsum);
+                g_m[j] = m_new;
             }
         }
-        bar_consumers();
+        bar_group(grp);
+        // ---- P.V: thread = (head j, dims 4*d4 .. 4*d4+3)
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int idx = tid + k * kConsumerThreads;
-            if (idx < kv_mul * 128) {
-                const int j = idx >> 7, d = idx & 127;
-                float a = __fmul_rn(acc[k], s_scale[j]);
-                for (int i = 0; i < cnt; ++i) a = __fmaf_rn(ssc[j * kChunk + i], Vt[i * 128 + d], a);
+        for (int k = 0; k < NACC; ++k) {
+            const int idx = gt + k * kAttnGT;
+            if (idx < KV_MUL * 32) {
+                const int j = idx >> 5, d4 = idx & 31;
+                const float scl = g_scale[j];
+                float4 a = acc[k];
+                a.x = __fmul_rn(a.x, scl); a.y = __fmul_rn(a.y, scl); a.z = __fmul_rn(a.z, scl); a.w = __fmul_rn(a.w, scl);
+                for (int i = 0; i < cnt; ++i) {
+                    const float pw = sc[j * 32 + i];
+                    const float4 vv = *reinterpret_cast<const float4*>(Vt + i * 128 + d4 * 4);
+                    a.x = __fmaf_rn(pw, vv.x, a.x); a.y = __fmaf_rn(pw, vv.y, a.y);
+                    a.z = __fmaf_rn(pw, vv.z, a.z); a.w = __fmaf_rn(pw, vv.w, a.w);
+                }
                 acc[k] = a;
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+        bar_group(grp); // sc / g_scale are rewritten by this group's next tile
+    };
+
+    int u = u0;
+    while (u < u1) {
+        const int kvh = u / nc;
+        const int seg_end = min(u1, (kvh + 1) * nc);
+        const bool own_last = seg_end == (kvh + 1) * nc; // the segment contains the KV head's last chunk
+        // ---- segment prologue (CTA-wide): q heads, and this step's K/V row if we own the last chunk
+        const int nraw = KV_MUL * 128 + (own_last ? 256 : 0);
+        bar_consumers();
+        for (int i = tid; i < nraw; i += kConsumerThreads) {
+            const float* src = i < KV_MUL * 128 ? p.qkv + (size_t) kvh * KV_MUL * 128 + i
+                               : i < KV_MUL * 128 + 128 ? p.qkv + p.Pl + (size_t) kvh * 128 + (i - KV_MUL * 128)
+                                                        : p.qkv + p.Pl + p.Kl + (size_t) kvh * 128 + (i - KV_MUL * 128 - 128);
+            raw[i] = __ldcg(src);
+        }
+        bar_consumers();
+        if (warp < KV_MUL + (own_last ? 1 : 0)) {
+            const float r = head_rscale_warp(raw + warp * 128, lane);
+            if (lane == 0) s_r[warp] = r;
+        }
+        bar_consumers();
+        for (int i = tid; i < nraw; i += kConsumerThreads) {
+            const int hd = i >> 7, e = i & 127;
+            if (hd < KV_MUL) {
+                sq[i] = head_norm_rope(raw + hd * 128, gq, p, s_r[hd], e);
+            } else {
+                const size_t coff = (((size_t) l * p.KVHl + kvh) * p.S + p.pos) * 128;
+                if (hd == KV_MUL) {
+                    const float kx = head_norm_rope(raw + hd * 128, gk, p, s_r[hd], e);
+                    sq[i] = kx;
+                    p.k_cache[coff + e] = kx;
+                } else {
+                    sq[i] = raw[i];
+                    p.v_cache[coff + e] = raw[i];
+                }
+            }
+        }
+        if (gt < 8) {
+            g_m[gt] = -INFINITY;
+            g_l[gt] = 0.0f;
+            g_scale[gt] = 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bar_consumers();
+        // ---- tiles of the segment: every warp walks every tile (ring protocol), its group works on every 4th
+        for (int uu = u; uu < seg_end; ++uu) {
+            const unsigned itx = it_base + (unsigned) (uu - u0);
+            const unsigned slot = itx % p.nslot, par = (itx / p.nslot) & 1;
+            mbar_wait(sh, p, sh.full + slot * 8, par, 4);
+            if (((uu - u) & (kAttnGroups - 1)) == grp) {
+                const int p0 = (uu - kvh * nc) * kChunk;
+                const int cnt = min(p.pos, p0 + kChunk) - p0; // cached positions in the tile
+                const float* Kt = reinterpret_cast<const float*>(sh.ring + (size_t) slot * kSlotBytes);
+                if (cnt > 0) tile(Kt, Kt + kChunk * 128, cnt);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+        }
+        if (own_last && grp == 0) tile(sq + KV_MUL * 128, sq + KV_MUL * 128 + 128, 1); // this step's own position
+        // ---- merge the 4 group states (online-softmax merge) and publish (m, l, acc) for the combine phase
+        bar_consumers();
+        float* red = raw; // [grp][head][132]; raw/sq are dead now
+        constexpr int HP = KV_MUL < 4 ? KV_MUL : 4; // heads per pass (scratch is 2560 floats)
+#pragma unroll
+        for (int h0 = 0; h0 < KV_MUL; h0 += HP) {
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) {
+                const int idx = gt + k * kAttnGT;
+                const int j = idx >> 5, d4 = idx & 31;
+                if (idx < KV_MUL * 32 && j >= h0 && j < h0 + HP)
+                    *reinterpret_cast<float4*>(red + (grp * HP + (j - h0)) * 132 + d4 * 4) = acc[k];
+            }
+            if (gt < HP) {
+                red[(grp * HP + gt) * 132 + 128] = g_m[h0 + gt];
+                red[(grp * HP + gt) * 132 + 129] = g_l[h0 + gt];
+            }
+            bar_consumers();
+            if (tid < HP * 128) {
+                const int j = tid >> 7, d = tid & 127;
+                float M = -INFINITY;
+#pragma unroll
+                for (int g = 0; g < kAttnGroups; ++g) M = fmaxf(M, red[(g * HP + j) * 132 + 128]);
+                float L = 0.0f, A = 0.0f;
+#pragma unroll
+                for (int g = 0; g < kAttnGroups; ++g) {
+                    const float mg = red[(g * HP + j) * 132 + 128];
+                    const float e = (mg == -INFINITY) ? 0.0f : expf(__fsub_rn(mg, M));
+                    L = __fmaf_rn(red[(g * HP + j) * 132 + 129], e, L);
+                    A = __fmaf_rn(red[(g * HP + j) * 132 + d], e, A);
+                }
+                const int h = kvh * KV_MUL + h0 + j;
+                const size_t slot = (size_t) h * gridDim.x + blockIdx.x;
+                p.part_acc[slot * 128 + d] = A;
+                if (d == 0) {
+                    p.part_m[slot] = M;
+                    p.part_l[slot] = L;
+                }
+            }
+            bar_consumers();
+        }
+        u = seg_end;
     }
-    if (cur >= 0) flush(cur);
+    it = it_base + (unsigned) (u1 - u0);
 }
 
-// merge the split-KV partials of each head, write fp32 att (debug) and its Q8_0 codes
+__device__ void consume_attn_dispatch(const Shared& sh, const MegaParams& p, int l, unsigned& it) {
+    switch (p.kv_mul) {
+        case 1: consume_attn<1>(sh, p, l, it); break;
+        case 2: consume_attn<2>(sh, p, l, it); break;
+        case 4: consume_attn<4>(sh, p, l, it); break;
+        default: consume_attn<8>(sh, p, l, it); break;
+    }
+}
+
+// merge the split-KV partials of each head (online-softmax merge), write fp32 att (debug
+// read-back) and its Q8_0 codes straight into the SG-layout vector the wo GEMV loads.
 __device__ void combine_attn(const Shared& sh, const MegaParams& p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* so = sh.scr + 2048 + 8 * kChunk;
+    float* mm = sh.scr;          // [kMaxGrid]
+    float* ww = sh.scr + 256;    // [kMaxGrid]
+    float* ll = sh.scr + 512;    // [kMaxGrid]
+    float* red = sh.scr + 768;   // [4][128]
+    float* so = sh.scr + 1280;   // [128]
     const int nc = p.pos / kChunk + 1;
     const long long U = (long long) p.KVHl * nc;
     const int G = gridDim.x;
     for (int h = blockIdx.x; h < p.Hl; h += G) {
         const int kvh = h / p.kv_mul;
         const long long ulo = (long long) kvh * nc, uhi = ulo + nc;
-        int blo = (int) (ulo * G / U) - 1, bhi = (int) (uhi * G / U) + 1;
-        blo = max(blo, 0);
-        bhi = min(bhi, G - 1);
+        const int blo = max((int) (ulo * G / U) - 1, 0), bhi = min((int) (uhi * G / U) + 1, G - 1);
+        const int nb = bhi - blo + 1;
+        bar_consumers();
+        if (tid < nb) {
+            const int b = blo + tid;
+            const long long s0 = U * b / G, s1 = U * (b + 1) / G;
+            const bool on = max(s0, ulo) < min(s1, uhi);
+            mm[tid] = on ? __ldcg(p.part_m + (size_t) h * G + b) : -INFINITY;
+            ll[tid] = on ? __ldcg(p.part_l + (size_t) h * G + b) : 0.0f;
+        }
+        bar_consumers();
+        float M = -INFINITY;
+        for (int i = 0; i < nb; ++i) M = fmaxf(M, mm[i]);
+        if (tid < nb) ww[tid] = (mm[tid] == -INFINITY) ? 0.0f : expf(__fsub_rn(mm[tid], M));
+        bar_consumers();
+        {
+            const int d = tid & 127, part = tid >> 7;
+            float A = 0.0f;
+            for (int i = part; i < nb; i += 4) {
+                const float w = ww[i];
+                if (w != 0.0f) A = __fmaf_rn(__ldcg(p.part_acc + ((size_t) h * G + blo + i) * 128 + d), w, A);
+            }
+            red[part * 128 + d] = A;
+        }
+        bar_consumers();
         if (tid < 128) {
-            float M = -INFINITY;
-            for (int b = blo; b <= bhi; ++b) {
-                const long long s0 = U * b / G, s1 = U * (b + 1) / G;
-                if (max(s0, ulo) < min(s1, uhi)) M = fmaxf(M, __ldcg(p.part_m + (size_t) h * G + b));
-            }
-            float Lsum = 0.0f, A = 0.0f;
-            for (int b = blo; b <= bhi; ++b) {
-                const long long s0 = U * b / G, s1 = U * (b + 1) / G;
-                if (max(s0, ulo) < min(s1, uhi)) {
-                    const size_t slot = (size_t) h * G + b;
-                    const float w = expf(__fsub_rn(__ldcg(p.part_m + slot), M));
-                    Lsum = __fmaf_rn(__ldcg(p.part_l + slot), w, Lsum);
-                    A = __fmaf_rn(__ldcg(p.part_acc + slot * 128 + tid), w, A);
-                }
-            }
+            float Lsum = 0.0f;
+            for (int i = 0; i < nb; ++i) Lsum = __fmaf_rn(ll[i], ww[i], Lsum);
+            const float A = __fadd_rn(__fadd_rn(red[tid], red[128 + tid]), __fadd_rn(red[256 + tid], red[384 + tid]));
             const float o = __fdiv_rn(A, Lsum);
             so[tid] = o;
             p.att[(size_t) h * 128 + tid] = o;
         }
         bar_consumers();
-        if (warp < 2) {
-            const float a = so[warp * 64 + lane], b = so[warp * 64 + 32 + lane];
-            const float scale = q8_scale(warp_max(fmaxf(fabsf(a), fabsf(b))));
-            p.att_q[(size_t) h * 128 + warp * 64 + lane] = (int8_t) q8_code(a, scale);
-            p.att_q[(size_t) h * 128 + warp * 64 + 32 + lane] = (int8_t) q8_code(b, scale);
-            if (lane == 0) p.att_s[h * 2 + warp] = scale;
-        }
-        bar_consumers();
+        if (warp < 2) put_group(p.att_q, h * 2 + warp, lane, so[warp * 64 + lane], so[warp * 64 + 32 + lane]);
     }
 }
 
@@ -577,11 +822,11 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
         // --- attention block (forward.c:254-298)
         prologue_norm_quant(sh, p, p.att_norm + (size_t) l * p.D, l == 0);
         stamp(p, l, 1);
-        consume_mat<1>(sh, p, ph_qkv(p, l), it, [&](int row, const float* v) { p.qkv[row] = v[0]; });
+        consume_mat<0>(sh, p, ph_qkv(p, l), it, p.qkv);
         stamp(p, l, 2);
         grid_barrier(sh, p, nbar);
         stamp(p, l, 3);
-        consume_attn(sh, p, l, it);
+        consume_attn_dispatch(sh, p, l, it);
         stamp(p, l, 4);
         grid_barrier(sh, p, nbar);
         stamp(p, l, 5);
@@ -589,24 +834,21 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
         stamp(p, l, 6);
         grid_barrier(sh, p, nbar);
         stamp(p, l, 7);
-        prologue_load_codes(sh, p.att_q, p.att_s, p.Pl);
-        consume_mat<1>(sh, p, ph_o(p, l), it,
-                       [&](int row, const float* v) { p.x[row] = __fadd_rn(__ldcg(p.x + row), v[0]); });
+        prologue_load_codes(sh, p.att_q, p.Pl);
+        consume_mat<1>(sh, p, ph_o(p, l), it, p.x);
         stamp(p, l, 8);
         grid_barrier(sh, p, nbar);
         stamp(p, l, 9);
         // --- feed-forward block (forward.c:303-338)
         prologue_norm_quant(sh, p, p.ffn_norm + (size_t) l * p.D, false);
         stamp(p, l, 10);
-        consume_mat<2>(sh, p, ph_13(p, l), it,
-                       [&](int row, const float* v) { p.h[row >> 1] = __fmul_rn(silu_ref(v[0]), v[1]); });
+        consume_mat<2>(sh, p, ph_13(p, l), it, p.h);
         stamp(p, l, 11);
         grid_barrier(sh, p, nbar);
         stamp(p, l, 12);
         prologue_quant_global(sh, p.h, p.Hdl);
         stamp(p, l, 13);
-        consume_mat<1>(sh, p, ph_2(p, l), it,
-                       [&](int row, const float* v) { p.x[row] = __fadd_rn(__ldcg(p.x + row), v[0]); });
+        consume_mat<1>(sh, p, ph_2(p, l), it, p.x);
         stamp(p, l, 14);
         grid_barrier(sh, p, nbar);
         stamp(p, l, 15);
@@ -615,7 +857,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
     // --- final norm + classifier (forward.c:344-348)
     prologue_norm_quant(sh, p, p.out_norm, p.layers_run == 0);
     stamp(p, p.L, 1);
-    consume_mat<1>(sh, p, ph_cls(p), it, [&](int row, const float* v) { p.logits[row] = v[0]; });
+    consume_mat<0>(sh, p, ph_cls(p), it, p.logits);
     stamp(p, p.L, 2);
 }
 
@@ -624,10 +866,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ 
     __shared__ int abort_flag;
     Shared sh;
     sh.ring = smem;
-    sh.xq = reinterpret_cast<int8_t*>(smem + p.off_xq);
-    sh.xs = reinterpret_cast<float*>(smem + p.off_xs);
+    sh.xq = smem + p.off_xq;
     sh.scr = reinterpret_cast<float*>(smem + p.off_scr);
-    sh.part = reinterpret_cast<float*>(smem + p.off_part);
     sh.misc = reinterpret_cast<float*>(smem + p.off_misc);
     sh.full = smem_u32(smem + p.off_bar);
     sh.empty = sh.full + kMaxSlots * 8;
@@ -680,22 +920,23 @@ int qw_mega_init(QwenCudaCtx* c) {
         return o;
     };
     // everything except the ring first, then give the ring all remaining slots
-    const int xq_b = amax, xs_b = amax / 64 * 4;
-    const int scr_b = std::max(c->D * 4, (2048 + 8 * kChunk + 128) * 4);
-    const int part_b = 2 * kPartFloats * 4, misc_b = 512, bar_b = 2 * kMaxSlots * 8;
-    const int fixed = ((xq_b + 127) & ~127) + ((xs_b + 127) & ~127) + ((scr_b + 127) & ~127) + ((part_b + 127) & ~127)
-                      + ((misc_b + 127) & ~127) + ((bar_b + 127) & ~127);
+    const int xq_b = (int) qw_row_bytes(amax);
+    const int scr_b = kScrFloats * 4;
+    const int misc_b = 1024, bar_b = 2 * kMaxSlots * 8;
+    const int fixed = ((xq_b + 127) & ~127) + ((scr_b + 127) & ~127) + ((misc_b + 127) & ~127) + ((bar_b + 127) & ~127);
     const int avail = dev_smem - fixed - 1024; // 1 KB left for static shared + driver reserve
     st->nslot = std::min(kMaxSlots, avail / kSlotBytes);
+    if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(st->nslot, atoi(e)));
+    if (const char* e = getenv("QWEN_MEGA_MODE")) st->dbg_mode = atoi(e);
+    if (const char* e = getenv("QWEN_MEGA_SPLIT")) st->copy_split = std::max(1, atoi(e));
+    if (getenv("QWEN_MEGA_VERBOSE")) fprintf(stderr, "[mega] nslot %d mode %d split %d smem %d\n", st->nslot, st->dbg_mode, st->copy_split, fixed);
     if (st->nslot < 2) {
         qw_set_error("persistent decode kernel: not enough shared memory for a 2-slot ring (%d bytes free)", avail);
         return -1;
     }
     take(st->nslot * kSlotBytes);
     st->off_xq = take(xq_b);
-    st->off_xs = take(xs_b);
     st->off_scr = take(scr_b);
-    st->off_part = take(part_b);
     st->off_misc = take(misc_b);
     st->off_bar = take(bar_b);
     st->smem = off;
@@ -707,8 +948,8 @@ int qw_mega_init(QwenCudaCtx* c) {
         return -1;
     }
     st->grid = c->num_sms;
-    QW_CUDA(cudaMalloc((void**) &st->att_q, qw_pad_cols(c->Pl)));
-    QW_CUDA(cudaMalloc((void**) &st->att_s, (size_t) qw_pad_cols(c->Pl) / 64 * 4));
+    QW_CUDA(cudaMalloc((void**) &st->att_q, qw_row_bytes(c->Pl)));
+    QW_CUDA(cudaMemset(st->att_q, 0, qw_row_bytes(c->Pl))); // pad groups stay zero
     QW_CUDA(cudaMalloc((void**) &st->part_m, (size_t) c->Hl * st->grid * 4));
     QW_CUDA(cudaMalloc((void**) &st->part_l, (size_t) c->Hl * st->grid * 4));
     QW_CUDA(cudaMalloc((void**) &st->part_acc, (size_t) c->Hl * st->grid * 128 * 4));
@@ -721,7 +962,7 @@ int qw_mega_init(QwenCudaCtx* c) {
 void qw_mega_free(QwenCudaCtx* c) {
     MegaState* st = state_of(c);
     if (!st) return;
-    void* bufs[] = {st->att_q, st->att_s, st->part_m, st->part_l, st->part_acc, st->prof};
+    void* bufs[] = {st->tlog, st->att_q, st->part_m, st->part_l, st->part_acc, st->prof};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete st;
@@ -745,12 +986,16 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.rope_cos = c->rope_cos; p.rope_sin = c->rope_sin;
     p.k_cache = c->k_cache; p.v_cache = c->v_cache;
     p.x = c->x; p.qkv = c->qkv; p.att = c->att; p.h = c->h; p.logits = c->logits;
-    p.att_q = st->att_q; p.att_s = st->att_s;
+    p.att_q = st->att_q;
     p.part_m = st->part_m; p.part_l = st->part_l; p.part_acc = st->part_acc;
     p.bar = c->bar_counter; p.bar_base = c->bar_epoch;
     p.err = c->err_flag;
+    p.dbg_mode = st->dbg_mode;
+    p.copy_split = st->copy_split;
     p.prof = st->prof;
-    p.nslot = st->nslot; p.off_xq = st->off_xq; p.off_xs = st->off_xs; p.off_scr = st->off_scr; p.off_part = st->off_part;
+    p.tlog = st->tlog;
+    p.tlog_warp = st->tlog_warp;
+    p.nslot = st->nslot; p.off_xq = st->off_xq; p.off_scr = st->off_scr;
     p.off_misc = st->off_misc; p.off_bar = st->off_bar;
     const int nbar = 6 * p.layers_run;
     c->bar_epoch += (unsigned long long) nbar * st->grid;
@@ -770,6 +1015,20 @@ int qw_mega_profile_enable(QwenCudaCtx* c) {
     QW_CUDA(cudaMemset(st->prof, 0, n * 8));
     QW_CUDA(cudaDeviceSynchronize());
     return (int) n;
+}
+int qw_mega_tlog(QwenCudaCtx* c, int warp, unsigned long long* host) {
+    MegaState* st = state_of(c);
+    if (!st || !st->grid) return -1;
+    if (!host) { // enable
+        if (!st->tlog) QW_CUDA(cudaMalloc((void**) &st->tlog, 4 * kTileLog * 8));
+        QW_CUDA(cudaMemset(st->tlog, 0, 4 * kTileLog * 8));
+        QW_CUDA(cudaDeviceSynchronize());
+        st->tlog_warp = warp;
+        return kTileLog;
+    }
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    QW_CUDA(cudaMemcpy(host, st->tlog, 4 * kTileLog * 8, cudaMemcpyDeviceToHost));
+    return kTileLog;
 }
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
     MegaState* st = state_of(c);
