@@ -178,7 +178,7 @@ extern "C" QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* m, int device,
         || dev_alloc(&c->aq, amax) || dev_alloc(&c->as, amax / 64) || dev_alloc(&c->token_dev, 1)
         || dev_alloc(&c->argmax_out, c->argmax_cap) || dev_alloc(&c->att_m, (size_t) c->Hl * c->att_max_splits)
         || dev_alloc(&c->att_l, (size_t) c->Hl * c->att_max_splits)
-        || dev_alloc(&c->att_acc, (size_t) c->Hl * c->att_max_splits * 128) || dev_alloc(&c->bar_counter, 8))
+        || dev_alloc(&c->att_acc, (size_t) c->Hl * c->att_max_splits * 128) || dev_alloc(&c->bar_counter, 512))
         return fail();
     // error flag lives in mapped pinned memory: the kernel writes it only on a barrier
     // timeout, the host reads it for free after every synchronise
@@ -276,7 +276,7 @@ static int qw_check_flag(QwenCudaCtx* c) {
     if (flag) {
         qw_set_error("decode kernel reported error %d (grid barrier timeout)", flag);
         *c->err_flag = 0;
-        cudaMemset(c->bar_counter, 0, 8); // the grid-barrier count is meaningless after an abort
+        cudaMemset(c->bar_counter, 0, 512 * 8); // the grid-barrier flags are meaningless after an abort
         c->bar_epoch = 0;
         return -3;
     }

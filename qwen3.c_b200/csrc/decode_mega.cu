@@ -155,14 +155,17 @@ __device__ __forceinline__ void mbar_wait(const Shared& sh, const MegaParams& p,
     }
 }
 
-// grid-wide barrier among the consumer threads of every CTA: bar.sync makes the CTA's writes
-// happen-before thread 0's release-add; the acquire poll + bar.sync hands the other CTAs'
-// writes to every thread here (readers use ld.cg / ld.acquire, never L1).
+// Grid-wide barrier among the consumer threads of every CTA: bar.sync orders the CTA's writes
+// before thread 0's release-add on one global counter; thread 0 polls it with ld.acquire and a
+// second bar.sync hands the other CTAs' writes to every thread here (readers use ld.cg /
+// ld.acquire afterwards, never L1). ~1.5 us on 148 CTAs, all of it L2 round trips. A variant
+// with one flag word per CTA and 148 polling threads per CTA was measured and is 3x SLOWER
+// (148 x 5 polled lines hot-spot the L2 slices), so the single counter stays.
 __device__ __forceinline__ void grid_barrier(const Shared& sh, const MegaParams& p, int& nbar) {
     bar_consumers();
     if (threadIdx.x == 0) {
         const unsigned long long target = p.bar_base + (unsigned long long) (nbar + 1) * gridDim.x;
-        red_release_add_u64(p.bar, 1ull); // release: orders the CTA's writes (seen through bar.sync) before the count
+        red_release_add_u64(p.bar, 1ull);
         unsigned long long t0 = 0;
         for (unsigned spin = 1; ld_acquire_u64(p.bar) < target; ++spin) {
             if ((spin & 1023u) == 0) {
@@ -412,7 +415,7 @@ __device__ __forceinline__ void zero_group(uint8_t* xq, int g, int lane) {
     if (lane == 0) *reinterpret_cast<float*>(xq + (g >> 2) * QW_SG_BYTES + 256 + (g & 3) * 4) = 0.0f;
 }
 
-constexpr int kMaxGroupsPerWarpNorm = 8; // D <= 8192
+constexpr int kMaxGroupsPerWarpNorm = 5; // D <= 5120 (Qwen3-32B); checked at init
 
 // x (fp32, D) -> RMSNorm with weights w -> Q8_0 codes + scales in shared memory (forward.c:254-259).
 // Warp w owns groups w, w+16, ...; all its loads are issued up front (one L2 round trip).
@@ -452,6 +455,17 @@ __device__ void prologue_norm_quant(const Shared& sh, const MegaParams& p, const
             }
         }
     }
+    // norm weights: issued now so their latency overlaps the reduction (no L1 in this kernel: 1-2 us under load)
+    float wa[kMaxGroupsPerWarpNorm], wb[kMaxGroupsPerWarpNorm];
+#pragma unroll
+    for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
+        const int g = warp + k * kConsumerWarps;
+        wa[k] = wb[k] = 0.0f;
+        if (g < groups) {
+            wa[k] = __ldg(w + g * 64 + lane);
+            wb[k] = __ldg(w + g * 64 + 32 + lane);
+        }
+    }
     float ss = 0.0f;
 #pragma unroll
     for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) ss = __fadd_rn(ss, __fadd_rn(__fmul_rn(va[k], va[k]), __fmul_rn(vb[k], vb[k])));
@@ -466,8 +480,8 @@ __device__ void prologue_norm_quant(const Shared& sh, const MegaParams& p, const
     for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
         const int g = warp + k * kConsumerWarps;
         if (g < groups) {
-            const float a = __fmul_rn(__ldg(w + g * 64 + lane), __fmul_rn(r, va[k]));
-            const float b = __fmul_rn(__ldg(w + g * 64 + 32 + lane), __fmul_rn(r, vb[k]));
+            const float a = __fmul_rn(wa[k], __fmul_rn(r, va[k]));
+            const float b = __fmul_rn(wb[k], __fmul_rn(r, vb[k]));
             put_group(sh.xq, g, lane, a, b);
         } else if (g < pad_groups) {
             zero_group(sh.xq, g, lane);
@@ -480,7 +494,7 @@ __device__ void prologue_norm_quant(const Shared& sh, const MegaParams& p, const
 __device__ void prologue_quant_global(const Shared& sh, const float* src, int n) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int groups = n / 64, pad_groups = qw_pad_cols(n) / 64;
-    constexpr int kBatch = 8;
+    constexpr int kBatch = 10; // Hd 9728 -> 152 groups -> 9.5 per warp: one round trip
     for (int g0 = warp; g0 < pad_groups; g0 += kBatch * kConsumerWarps) {
         float va[kBatch], vb[kBatch];
 #pragma unroll
@@ -772,13 +786,29 @@ __device__ void combine_attn(const Shared& sh, const MegaParams& p) {
         const long long ulo = (long long) kvh * nc, uhi = ulo + nc;
         const int blo = max((int) (ulo * G / U) - 1, 0), bhi = min((int) (uhi * G / U) + 1, G - 1);
         const int nb = bhi - blo + 1;
-        bar_consumers();
+        // all global loads of this head are issued up front (one L2 round trip): m, l by the first nb
+        // threads, the nb partial accumulators by (dim, part) threads, 4 parts x up to 8 each
+        const int d = tid & 127, part = tid >> 7;
+        constexpr int kMaxPer = 8;
+        float av[kMaxPer];
+#pragma unroll
+        for (int k = 0; k < kMaxPer; ++k) {
+            const int i = part + 4 * k;
+            av[k] = i < nb ? __ldcg(p.part_acc + ((size_t) h * G + blo + i) * 128 + d) : 0.0f;
+        }
+        float my_m = -INFINITY, my_l = 0.0f;
         if (tid < nb) {
             const int b = blo + tid;
             const long long s0 = U * b / G, s1 = U * (b + 1) / G;
-            const bool on = max(s0, ulo) < min(s1, uhi);
-            mm[tid] = on ? __ldcg(p.part_m + (size_t) h * G + b) : -INFINITY;
-            ll[tid] = on ? __ldcg(p.part_l + (size_t) h * G + b) : 0.0f;
+            if (max(s0, ulo) < min(s1, uhi)) {
+                my_m = __ldcg(p.part_m + (size_t) h * G + b);
+                my_l = __ldcg(p.part_l + (size_t) h * G + b);
+            }
+        }
+        bar_consumers(); // scratch free
+        if (tid < nb) {
+            mm[tid] = my_m;
+            ll[tid] = my_l;
         }
         bar_consumers();
         float M = -INFINITY;
@@ -786,9 +816,13 @@ __device__ void combine_attn(const Shared& sh, const MegaParams& p) {
         if (tid < nb) ww[tid] = (mm[tid] == -INFINITY) ? 0.0f : expf(__fsub_rn(mm[tid], M));
         bar_consumers();
         {
-            const int d = tid & 127, part = tid >> 7;
             float A = 0.0f;
-            for (int i = part; i < nb; i += 4) {
+#pragma unroll
+            for (int k = 0; k < kMaxPer; ++k) {
+                const int i = part + 4 * k;
+                if (i < nb && ww[i] != 0.0f) A = __fmaf_rn(av[k], ww[i], A); // stale slots have weight 0 and are skipped
+            }
+            for (int i = part + 4 * kMaxPer; i < nb; i += 4) { // very long merges (few KV heads per GPU)
                 const float w = ww[i];
                 if (w != 0.0f) A = __fmaf_rn(__ldcg(p.part_acc + ((size_t) h * G + blo + i) * 128 + d), w, A);
             }
@@ -906,6 +940,11 @@ int qw_mega_init(QwenCudaCtx* c) {
         qw_set_error("persistent decode kernel: a weight row (%d columns) does not fit one %d-byte ring slot", amax, kSlotBytes);
         return -1;
     }
+    if (qw_pad_cols(c->D) / 64 > kMaxGroupsPerWarpNorm * kConsumerWarps) {
+        qw_set_error("persistent decode kernel: dim %d exceeds the fused RMSNorm prologue's %d columns", c->D,
+                     kMaxGroupsPerWarpNorm * kConsumerWarps * 64);
+        return -1;
+    }
     int dev_smem = 0, coop = 0;
     QW_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     QW_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
@@ -953,7 +992,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     QW_CUDA(cudaMalloc((void**) &st->part_m, (size_t) c->Hl * st->grid * 4));
     QW_CUDA(cudaMalloc((void**) &st->part_l, (size_t) c->Hl * st->grid * 4));
     QW_CUDA(cudaMalloc((void**) &st->part_acc, (size_t) c->Hl * st->grid * 128 * 4));
-    QW_CUDA(cudaMemset(c->bar_counter, 0, 8));
+    QW_CUDA(cudaMemset(c->bar_counter, 0, 512 * 8)); // one flag word per CTA
     c->bar_epoch = 0;
     c->path = 0;
     return 0;
