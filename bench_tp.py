@@ -1,0 +1,79 @@
+"""Tensor-parallel arm of bench.py (N > 1): one process per GPU under torchrun, NCCL all-reduce
+after wo / w2 and an all-gather of the logits. Strong scaling: the same
+8B-shape decode at context 4096 on 2, 4 or 8 GPUs."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+
+def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from bench import ClockSampler, ensure_ckpt, log, measured_peak
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ["QWEN_CUDA_DEVICE"] = str(local)
+    os.environ["QWEN_CUDA_TP_RANK"] = str(rank)
+    os.environ["QWEN_CUDA_TP_SIZE"] = str(world)
+    seq_len = ctx + W + K + 8
+    if rank == 0:
+        ensure_ckpt(pkg, shape_name)
+    dist.barrier()
+    path = ensure_ckpt(pkg, shape_name)
+    ql = pkg.QwenLib()
+    t = time.time()
+    gm = ql.open(path, seq_len)
+    pkg.tp.init_tensor_parallel(ql, gm, rank, world, dist)
+    if rank == 0:
+        log(f"[bench] tp={world} model_create + nccl init {time.time() - t:.1f}s")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev = torch.device("cuda", local)
+
+    def max_over_ranks(x: float) -> float:
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms, launches = gm.time_decode(7, ctx, K, W)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = max_over_ranks(ms)
+    for i in range(W):
+        gm.forward_nocopy(7, ctx + i)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        if not gm.forward_nocopy(7, ctx + W + i):
+            raise SystemExit("forward failed: " + ql.err())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        tok_s = K / (ms / 1e3)
+        bytes_tok = float(np.mean([shape.decode_bytes(ctx + W + i) for i in range(K)]))
+        peak, peak_src = measured_peak()
+        achieved = bytes_tok / world * tok_s / 1e9  # per-GPU share of the algorithmic bytes
+        line = dict(base, value=tok_s, ms_per_step=ms / K, dtype="int8xint8->int32, fp32", clocks=clocks,
+                    gpu_launches=launches + K * (2 * shape.n_layers + 1),
+                    e2e={"value": K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": shape.vocab_size * 4},
+                    roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "traffic": None, "peak_source": peak_src, "bytes_per_token": bytes_tok,
+                              "kernel": "per-op kernels + NCCL all-reduce (the persistent kernel is single-GPU in round 1)"})
+        line["config"]["parallelism"] = f"tp{world}"
+        line["config"]["path"] = "ops+nccl"
+        print(json.dumps(line), flush=True)
+    gm.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

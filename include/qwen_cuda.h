@@ -78,6 +78,12 @@ QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* desc, int device, QwenCud
 /* Stands behind model_free (reference: src/model.c:491-500). NULL-safe. */
 void qwen_cuda_destroy(QwenCudaCtx* ctx);
 
+/* Tensor parallelism, one process per GPU (no reference counterpart: the reference is single
+ * process). Rank 0 makes an id, the caller's own rendezvous hands the same 128
+ * bytes to every rank, each rank then joins. Contexts with tp.size == 1 need neither. */
+int qwen_cuda_tp_unique_id(void* out128);
+int qwen_cuda_tp_init(QwenCudaCtx* ctx, const void* id128);
+
 /* Pinned host memory for state.logits (reference: src/model.c:342 callocs it). */
 void* qwen_cuda_host_alloc(size_t bytes);
 void qwen_cuda_host_free(void* p);

@@ -5,5 +5,5 @@ CUDA). This Python package only holds what surrounds it: the build driver, a cty
 mirror of the reference's operator interface (include/forward.h, q8.h, model.h) and the
 synthetic-checkpoint writer used by tests and bench.py.
 """
-from . import binding, build, checkpoint  # noqa: F401
+from . import binding, build, checkpoint, tp  # noqa: F401
 from .binding import B200Model, QwenLib  # noqa: F401

@@ -199,3 +199,44 @@ def ensure_checkpoint(directory: str, shape_name: str, seed: int = 1234, mode: s
     if not (os.path.exists(path) and os.path.getsize(path) == shape.file_bytes()):
         write_checkpoint(path, shape, seed=seed, mode=mode, **kw)
     return path
+
+
+def load_views(path: str) -> dict:
+    """Memory-map a `.bin` and return its header fields plus numpy views of every tensor in export
+    order (reference reader: src/model.c:59-244). Used by the tensor-parallel host logic and tests."""
+    hdr = np.fromfile(path, dtype="<i4", count=12)
+    assert hdr[0] == MAGIC and hdr[1] == VERSION, "not a qwen3.c checkpoint"
+    D, Hd, L, H, KVH, V, S, hd, shared, G = (int(x) for x in hdr[2:12])
+    P, K = H * hd, KVH * hd
+    mm = np.memmap(path, dtype=np.uint8, mode="r")
+    off = 256
+    out = dict(dim=D, hidden_dim=Hd, n_layers=L, n_heads=H, n_kv_heads=KVH, vocab_size=V, seq_len=S, head_dim=hd,
+               shared_classifier=shared, group_size=G)
+
+    def f32(n):
+        nonlocal off
+        a = mm[off: off + 4 * n].view(np.float32)
+        off += 4 * n
+        return a
+
+    def q8(rows, cols):
+        nonlocal off
+        n = rows * cols
+        q = mm[off: off + n].view(np.int8).reshape(rows, cols)
+        off += n
+        s = mm[off: off + 4 * (n // G)].view(np.float32).reshape(rows, cols // G)
+        off += 4 * (n // G)
+        return q, s
+
+    out["att_norm"] = f32(L * D).reshape(L, D)
+    out["ffn_norm"] = f32(L * D).reshape(L, D)
+    out["out_norm"] = f32(D)
+    out["q_norm"] = f32(L * hd).reshape(L, hd)
+    out["k_norm"] = f32(L * hd).reshape(L, hd)
+    out["emb"] = q8(V, D)
+    for name, rows, cols in (("wq", P, D), ("wk", K, D), ("wv", K, D), ("wo", D, P), ("w1", Hd, D), ("w2", D, Hd),
+                             ("w3", Hd, D)):
+        out[name] = [q8(rows, cols) for _ in range(L)]
+    out["cls"] = out["emb"] if shared else q8(V, D)
+    assert off == mm.size, (off, mm.size)
+    return out

@@ -156,6 +156,8 @@ struct QwenCudaCtx {
     unsigned long long bar_epoch;
     int* err_flag;
 
+    void* nccl_comm;  // tensor-parallel communicator (tp_nccl.cu), NULL when tp_size == 1
+    float* logits_all; // [V] gathered logits on tensor-parallel contexts
     void* mega;       // persistent-kernel state (decode_mega.cu)
     int layers_run;   // debug: run only the first n layers (-1 = all)
     float* logits_pinned; // optional pinned bounce buffer
@@ -175,4 +177,7 @@ int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos);
 int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos);
 int qw_mega_init(QwenCudaCtx* c);
 void qw_mega_free(QwenCudaCtx* c);
+int qw_tp_allreduce(QwenCudaCtx* c, float* buf, size_t n);
+int qw_tp_allgather(QwenCudaCtx* c, const float* src, float* dst, size_t n_per_rank);
+void qw_tp_free(QwenCudaCtx* c);
 void launch_argmax(const float* v, int n, int* out, int* also, cudaStream_t st);

@@ -191,6 +191,7 @@ extern "C" QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* m, int device,
         qw_set_error("qwen_cuda_create: pinned logits buffer allocation failed");
         return fail();
     }
+    if (tp.size > 1 && dev_alloc(&c->logits_all, c->V)) return fail();
     if (qw_mega_init(c)) return fail();
     // dev_alloc's memsets run on the legacy default stream, which does NOT order against our
     // non-blocking stream: without this a late memset can zero buffers the first step already wrote
@@ -206,6 +207,8 @@ extern "C" void qwen_cuda_destroy(QwenCudaCtx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     qw_mega_free(c);
+    qw_tp_free(c);
+    if (c->logits_all) cudaFree(c->logits_all);
     if (c->w_emb != c->w_cls) cudaFree(c->w_emb);
     void* bufs[] = {c->w_qkv, c->w_o, c->w_13, c->w_2, c->w_cls, c->att_norm, c->ffn_norm, c->out_norm, c->q_norm,
                     c->k_norm, c->rope_cos, c->rope_sin, c->k_cache, c->v_cache, c->x, c->xb, c->qkv, c->q, c->att,
@@ -297,9 +300,9 @@ extern "C" int qwen_cuda_sync(QwenCudaCtx* c) {
 
 extern "C" int qwen_cuda_logits_to_host(QwenCudaCtx* c, float* logits_host) {
     if (!c || !logits_host) return -2;
-    // each rank owns vocab rows [rank*Vl, (rank+1)*Vl) (classifier is column-parallel over V)
-    QW_CUDA(cudaMemcpyAsync(logits_host + (size_t) c->tp_rank * c->Vl, c->logits, (size_t) c->Vl * sizeof(float),
-                            cudaMemcpyDeviceToHost, c->stream));
+    // tensor-parallel contexts hold the all-gathered logits (the classifier is split over vocab rows)
+    const float* src = c->tp_size > 1 ? c->logits_all : c->logits;
+    QW_CUDA(cudaMemcpyAsync(logits_host, src, (size_t) c->V * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     QW_CUDA(cudaStreamSynchronize(c->stream));
     return qw_check_flag(c);
 }
@@ -312,7 +315,7 @@ extern "C" int qwen_cuda_forward(QwenCudaCtx* c, int token, int pos, float* logi
 }
 
 extern "C" int qwen_cuda_decode_greedy(QwenCudaCtx* c, int first_token, int pos0, int n, int* out_tokens_host) {
-    if (!c || n < 0 || n > c->argmax_cap || c->tp_size != 1) {
+    if (!c || n < 0 || n > c->argmax_cap) {
         qw_set_error("decode_greedy: bad arguments (n %d, cap %d, tp %d)", n, c ? c->argmax_cap : 0, c ? c->tp_size : 0);
         return -2;
     }
@@ -320,7 +323,7 @@ extern "C" int qwen_cuda_decode_greedy(QwenCudaCtx* c, int first_token, int pos0
     QW_CUDA(cudaMemcpyAsync(c->token_dev, &first_token, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     for (int i = 0; i < n; ++i) {
         if (int rc = step(c, 0, c->token_dev, pos0 + i)) return rc;
-        launch_argmax(c->logits, c->Vl, c->argmax_out + i, c->token_dev, c->stream);
+        launch_argmax(c->tp_size > 1 ? c->logits_all : c->logits, c->V, c->argmax_out + i, c->token_dev, c->stream);
     }
     QW_CUDA(cudaMemcpyAsync(out_tokens_host, c->argmax_out, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     return qwen_cuda_sync(c);

@@ -175,10 +175,6 @@ int qw_attention_device(QwenCudaCtx* c, int layer, int pos, const float* q_dev, 
 int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     cudaStream_t st = c->stream;
     const int D = c->D, Pl = c->Pl, Kl = c->Kl, Hdl = c->Hdl;
-    if (c->tp_size != 1) {
-        qw_set_error("per-op decode path is single-GPU only");
-        return -2;
-    }
     k_embed<<<(D + 255) / 256, 256, 0, st>>>(c->x, c->w_emb, token, token_dev, D);
     const int layers = (c->layers_run >= 0 && c->layers_run <= c->L) ? c->layers_run : c->L;
     for (int l = 0; l < layers; ++l) {
@@ -192,6 +188,7 @@ int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         if (qw_attention_device(c, l, pos, c->q, c->att)) return -1;
         quantize_padded(c, c->att, Pl);
         launch_gemv_sg(c->w_o + l * c->w_o_stride, c->aq, c->as, c->xb, D, Pl, nullptr, st);
+        if (qw_tp_allreduce(c, c->xb, D)) return -1; // wo is row-parallel: partial sums over the head slices
         k_add<<<(D + 255) / 256, 256, 0, st>>>(c->x, c->xb, D);
         launch_rmsnorm(c->xb, c->x, c->ffn_norm + (size_t) l * D, D, st);
         quantize_padded(c, c->xb, D);
@@ -199,14 +196,16 @@ int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         k_swiglu_pairs<<<(Hdl + 255) / 256, 256, 0, st>>>(c->h, c->h13, Hdl);
         quantize_padded(c, c->h, Hdl);
         launch_gemv_sg(c->w_2 + l * c->w_2_stride, c->aq, c->as, c->xb, D, Hdl, nullptr, st);
+        if (qw_tp_allreduce(c, c->xb, D)) return -1; // w2 is row-parallel over the hidden slices
         k_add<<<(D + 255) / 256, 256, 0, st>>>(c->x, c->xb, D);
     }
     launch_rmsnorm(c->x, c->x, c->out_norm, D, st);
     quantize_padded(c, c->x, D);
     launch_gemv_sg(c->w_cls, c->aq, c->as, c->logits, c->Vl, D, nullptr, st);
+    if (c->tp_size > 1 && qw_tp_allgather(c, c->logits, c->logits_all, c->Vl)) return -1; // classifier is split over V
     QW_CUDA(cudaGetLastError());
     return 0;
 }
 
 // launches per token on this path (for bench.py's gpu_launches claim)
-int qw_decode_ops_launches(const QwenCudaCtx* c) { return 1 + c->L * 14 + 3; }
+int qw_decode_ops_launches(const QwenCudaCtx* c) { return 1 + c->L * 14 + 3; } // + 2 NCCL kernels per layer when tp_size > 1

@@ -10,6 +10,8 @@
  * Environment (no new CLI flags, so examples/qwen.c stays untouched):
  *   QWEN_CUDA_DEVICE   device ordinal, default 0
  *   QWEN_CUDA_PATH     "ops" selects the one-kernel-per-op debug path
+ *   QWEN_CUDA_TP_RANK / QWEN_CUDA_TP_SIZE   tensor-parallel placement of this process (one process per
+ *                      GPU); the caller then hands every rank the same NCCL id via qwen_cuda_tp_init
  */
 #include <errno.h>
 #include <fcntl.h>
@@ -219,6 +221,12 @@ Model* model_create(const char* path, int override_seq_len) {
         d.rope_cos = rc; d.rope_sin = rs;
         const char* dev = getenv("QWEN_CUDA_DEVICE");
         QwenCudaTp tp = {0, 1};
+        const char* tr = getenv("QWEN_CUDA_TP_RANK");
+        const char* ts = getenv("QWEN_CUDA_TP_SIZE");
+        if (tr && ts) {
+            tp.rank = atoi(tr);
+            tp.size = atoi(ts);
+        }
         ctx = qwen_cuda_create(&d, dev ? atoi(dev) : 0, tp);
     }
     free(dq); free(dk); free(dv); free(dox); free(d1); free(d2); free(d3); free(rc); free(rs);

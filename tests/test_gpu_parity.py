@@ -334,3 +334,20 @@ def test_06b_shape_logits_match_oracle(qlib, oracle, pkg, ckpt_dir):
     toks = [11, 4711, 151935, 0, 90210, 7, 7, 1234]
     stats, _, _ = parity_run(qlib, oracle, path, toks, 32, 0)
     check_parity_stats(stats)
+
+
+def test_tensor_parallel_2gpu_matches_single_gpu(qlib, pkg, ckpt_dir):
+    """TP=2 over NCCL (one process per GPU) against TP=1 on the same checkpoint and tokens: same
+    greedy tokens, logits within the flip-noise bound. Needs 2 visible GPUs (gpurun --gpus 2)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "small", seed=11)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531",
+                          os.path.join(root, "tests", "tp_gpu_worker.py"), path],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0 and "TP_GPU_OK" in out.stdout, out.stdout[-3000:]
