@@ -55,6 +55,7 @@ constexpr int kProfSlots = 16; // per layer: stamps after each phase step (CTA-l
 struct MegaParams {
     int D, Hdl, L, Hl, KVHl, Pl, Kl, Vl, S, kv_mul;
     int pos, token, layers_run;
+    int perm; // CTA -> row-block permutation multiplier (coprime to the grid)
     int copy_split; // debug: issue each tile as this many bulk copies
     int dbg_mode; // 0 normal; 1 consumers skip the GEMV math (ring throughput test); 2 skip attention math too
     const int* token_dev;
@@ -77,7 +78,7 @@ struct MegaParams {
 struct MegaState {
     uint8_t* att_q = nullptr;
     float *part_m = nullptr, *part_l = nullptr, *part_acc = nullptr;
-    int grid = 0, nslot = 0, dbg_mode = 0, copy_split = 1;
+    int grid = 0, nslot = 0, dbg_mode = 0, copy_split = 1, perm = 1;
     unsigned long long* prof = nullptr;
     unsigned long long* tlog = nullptr;
     int tlog_warp = 0;
@@ -187,28 +188,38 @@ __device__ __forceinline__ void grid_barrier(const Shared& sh, const MegaParams&
 struct MatPhase {
     const uint8_t* base;
     int rows, n, gran;
+    int perm = 1;
 };
 __device__ __forceinline__ void cta_rows(const MatPhase& m, int& r0, int& r1) {
     const long long units = m.rows / m.gran;
-    r0 = (int) (units * blockIdx.x / gridDim.x) * m.gran;
-    r1 = (int) (units * (blockIdx.x + 1) / gridDim.x) * m.gran;
+    // CTA -> row-block map: a multiplicative permutation (perm coprime to the grid). With the identity
+    // map the GEMV phases ran 8-10 % slower and a fixed third of the CTAs arrived 2-4 us late at every
+    // barrier (measured, profiles/r1_k_decode_summary.md); any scattering permutation removes that.
+    const int b = (int) ((blockIdx.x * (unsigned) m.perm) % gridDim.x);
+    r0 = (int) (units * b / gridDim.x) * m.gran;
+    r1 = (int) (units * (b + 1) / gridDim.x) * m.gran;
 }
 __device__ __forceinline__ int rows_per_tile(const MatPhase& m) {
     int rt = kSlotBytes / (int) qw_row_bytes(m.n);
     if (rt >= 2) rt &= ~1; // whole 2-row units per tile
     return rt < m.gran ? m.gran : rt;
 }
-__device__ __forceinline__ MatPhase ph_qkv(const MegaParams& p, int l) { return {p.w_qkv + l * p.s_qkv, p.Pl + 2 * p.Kl, p.D, 1}; }
-__device__ __forceinline__ MatPhase ph_o(const MegaParams& p, int l) { return {p.w_o + l * p.s_o, p.D, p.Pl, 1}; }
-__device__ __forceinline__ MatPhase ph_13(const MegaParams& p, int l) { return {p.w_13 + l * p.s_13, 2 * p.Hdl, p.D, 2}; }
-__device__ __forceinline__ MatPhase ph_2(const MegaParams& p, int l) { return {p.w_2 + l * p.s_2, p.D, p.Hdl, 1}; }
-__device__ __forceinline__ MatPhase ph_cls(const MegaParams& p) { return {p.w_cls, p.Vl, p.D, 1}; }
+__device__ __forceinline__ MatPhase ph_qkv(const MegaParams& p, int l) { return {p.w_qkv + l * p.s_qkv, p.Pl + 2 * p.Kl, p.D, 1, p.perm}; }
+__device__ __forceinline__ MatPhase ph_o(const MegaParams& p, int l) { return {p.w_o + l * p.s_o, p.D, p.Pl, 1, p.perm}; }
+__device__ __forceinline__ MatPhase ph_13(const MegaParams& p, int l) { return {p.w_13 + l * p.s_13, 2 * p.Hdl, p.D, 2, p.perm}; }
+__device__ __forceinline__ MatPhase ph_2(const MegaParams& p, int l) { return {p.w_2 + l * p.s_2, p.D, p.Hdl, 1, p.perm}; }
+__device__ __forceinline__ MatPhase ph_cls(const MegaParams& p) { return {p.w_cls, p.Vl, p.D, 1, p.perm}; }
 
+// index of the unit block this CTA attends over (also the slot of its partial results)
+__device__ __forceinline__ int attn_block(const MegaParams& p) {
+    return (int) ((blockIdx.x * (unsigned) p.perm) % gridDim.x);
+}
 __device__ __forceinline__ void attn_units(const MegaParams& p, int& nc, int& u0, int& u1) {
     nc = p.pos / kChunk + 1;
     const long long U = (long long) p.KVHl * nc;
-    u0 = (int) (U * blockIdx.x / gridDim.x);
-    u1 = (int) (U * (blockIdx.x + 1) / gridDim.x);
+    const int b = attn_block(p);
+    u0 = (int) (U * b / gridDim.x);
+    u1 = (int) (U * (b + 1) / gridDim.x);
 }
 
 // ---------------------------------------------------------------- producer
@@ -531,12 +542,18 @@ constexpr int kScrFloats = kScrS + 4 * 8 * 32;
 
 // RMSNorm weight + RoPE for element i of a 128-wide head (forward.c:267-280, 104-118);
 // cos/sin come from the host-computed table so the angles are the reference's bit for bit.
-__device__ __forceinline__ float head_norm_rope(const float* raw, const float* g, const MegaParams& p, float r, int i) {
+struct RopeCoef { // this thread's constants for element i of any head: loaded once per attention phase
+    float c, s, glo, ghi;
+};
+__device__ __forceinline__ RopeCoef rope_coef(const float* g, const MegaParams& p, int i) {
     const int j = i & 63;
-    const float c = __ldg(p.rope_cos + (size_t) p.pos * 64 + j), s = __ldg(p.rope_sin + (size_t) p.pos * 64 + j);
-    const float a = __fmul_rn(__ldg(g + j), __fmul_rn(r, raw[j]));
-    const float b = __fmul_rn(__ldg(g + j + 64), __fmul_rn(r, raw[j + 64]));
-    return (i < 64) ? __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, s)) : __fadd_rn(__fmul_rn(a, s), __fmul_rn(b, c));
+    return {__ldg(p.rope_cos + (size_t) p.pos * 64 + j), __ldg(p.rope_sin + (size_t) p.pos * 64 + j), __ldg(g + j), __ldg(g + j + 64)};
+}
+__device__ __forceinline__ float head_norm_rope(const float* raw, const RopeCoef& k, float r, int i) {
+    const int j = i & 63;
+    const float a = __fmul_rn(k.glo, __fmul_rn(r, raw[j]));
+    const float b = __fmul_rn(k.ghi, __fmul_rn(r, raw[j + 64]));
+    return (i < 64) ? __fsub_rn(__fmul_rn(a, k.c), __fmul_rn(b, k.s)) : __fadd_rn(__fmul_rn(a, k.s), __fmul_rn(b, k.c));
 }
 // sum of squares over 128 values by one warp (4 per lane, then the shuffle tree)
 __device__ __forceinline__ float head_rscale_warp(const float* raw, int lane) {
@@ -583,6 +600,9 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
     const float inv = sqrtf(128.0f);
     const unsigned it_base = it;
     float4 acc[NACC];
+    // element e = tid & 127 is the one this thread normalises/rotates for every head (the strides are
+    // multiples of 128): fetch its cos/sin and norm weights now, off the critical path (no L1 here)
+    const RopeCoef kq = rope_coef(gq, p, tid & 127), kk = rope_coef(gk, p, tid & 127);
 
     // one tile: cnt positions, K rows at Kt, V rows at Vt (shared memory)
     auto tile = [&](const float* Kt, const float* Vt, int cnt) {
@@ -678,11 +698,11 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
         for (int i = tid; i < nraw; i += kConsumerThreads) {
             const int hd = i >> 7, e = i & 127;
             if (hd < KV_MUL) {
-                sq[i] = head_norm_rope(raw + hd * 128, gq, p, s_r[hd], e);
+                sq[i] = head_norm_rope(raw + hd * 128, kq, s_r[hd], e);
             } else {
                 const size_t coff = (((size_t) l * p.KVHl + kvh) * p.S + p.pos) * 128;
                 if (hd == KV_MUL) {
-                    const float kx = head_norm_rope(raw + hd * 128, gk, p, s_r[hd], e);
+                    const float kx = head_norm_rope(raw + hd * 128, kk, s_r[hd], e);
                     sq[i] = kx;
                     p.k_cache[coff + e] = kx;
                 } else {
@@ -746,7 +766,7 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
                     A = __fmaf_rn(red[(g * HP + j) * 132 + d], e, A);
                 }
                 const int h = kvh * KV_MUL + h0 + j;
-                const size_t slot = (size_t) h * gridDim.x + blockIdx.x;
+                const size_t slot = (size_t) h * gridDim.x + attn_block(p);
                 p.part_acc[slot * 128 + d] = A;
                 if (d == 0) {
                     p.part_m[slot] = M;
@@ -987,6 +1007,13 @@ int qw_mega_init(QwenCudaCtx* c) {
         return -1;
     }
     st->grid = c->num_sms;
+    {
+        auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+        int k = std::max(1, st->grid / 3);
+        while (gcd(k, st->grid) != 1) ++k;
+        st->perm = k;
+        if (const char* e = getenv("QWEN_MEGA_PERM")) { const int v = atoi(e); if (v > 0 && gcd(v, st->grid) == 1) st->perm = v; }
+    }
     QW_CUDA(cudaMalloc((void**) &st->att_q, qw_row_bytes(c->Pl)));
     QW_CUDA(cudaMemset(st->att_q, 0, qw_row_bytes(c->Pl))); // pad groups stay zero
     QW_CUDA(cudaMalloc((void**) &st->part_m, (size_t) c->Hl * st->grid * 4));
@@ -1030,6 +1057,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.bar = c->bar_counter; p.bar_base = c->bar_epoch;
     p.err = c->err_flag;
     p.dbg_mode = st->dbg_mode;
+    p.perm = st->perm;
     p.copy_split = st->copy_split;
     p.prof = st->prof;
     p.tlog = st->tlog;

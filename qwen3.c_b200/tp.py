@@ -1,7 +1,7 @@
 """Tensor-parallel host logic (one process per GPU), SURVEY.md section 8e.
 
-The reference is single process; TP is a new capability whose oracle is the single-GPU / CPU
-forward. Sharding (identical to what qwen_cuda_create does at upload, csrc/context.cu):
+The reference is single process; TP is a new capability that must reproduce the
+single-GPU forward. Sharding (identical to what qwen_cuda_create does at upload, csrc/context.cu):
 
   column-parallel = contiguous ROW blocks of the [out][in] tensors, groups stay whole:
       wq by query head, wk/wv by kv head, w1/w3 and the classifier by rows;

@@ -351,3 +351,27 @@ def test_tensor_parallel_2gpu_matches_single_gpu(qlib, pkg, ckpt_dir):
                           os.path.join(root, "tests", "tp_gpu_worker.py"), path],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert out.returncode == 0 and "TP_GPU_OK" in out.stdout, out.stdout[-3000:]
+
+
+def test_quantize_fast_path_bit_exact_on_many_values(qlib, oracle):
+    """4M values, half of the groups seeded with values one ulp either side of k+0.5 after division:
+    the device quantiser (IEEE division + roundf) must give the oracle's codes bit for bit. (A
+    reciprocal-multiply variant with an exact fallback was also bit-exact here but slower.)"""
+    rng = np.random.default_rng(123)
+    n = 64 * 65536
+    x = rng.standard_normal(n).astype(np.float32) * rng.choice([1e-4, 0.3, 7.0, 900.0], size=n).astype(np.float32)
+    g = x.reshape(-1, 64)
+    # half the groups: put values exactly on / next to rounding boundaries of that group's scale
+    amax = np.abs(g).max(axis=1)
+    scale = (amax / np.float32(127.0)).astype(np.float32)
+    ks = rng.integers(-126, 126, size=g.shape).astype(np.float32) + np.float32(0.5)
+    near = (ks * scale[:, None]).astype(np.float32)
+    near = np.nextafter(near, np.where(rng.random(g.shape) < 0.5, np.float32(np.inf), np.float32(-np.inf))).astype(np.float32)
+    mask = (np.arange(g.shape[0]) % 2 == 0)[:, None] & (np.abs(near) < amax[:, None])
+    mask[:, 0] = False
+    g = np.where(mask, near, g)
+    x = np.ascontiguousarray(g.reshape(-1), np.float32)
+    q, s = qlib.q8_quantize(x)
+    oq, os_ = oracle.q8_quantize(x)
+    same(s, os_)
+    same(q, oq)
