@@ -137,6 +137,12 @@ int qwen_cuda_matmul(float* out, const int8_t* xq, const float* xs, const int8_t
                      int n, int d, int group);                                           /* forward.c:79-101 */
 /* Test hook: the exact int32 dot of every (row, group), dots[d][n/group]. */
 int qwen_cuda_matmul_group_dots(int32_t* dots, const int8_t* xq, const int8_t* wq, int n, int d, int group);
+/* Batched matmul for prefill: T tokens at once on the tcgen05 tensor cores (csrc/prefill_gemm.cu).
+ * Same arithmetic as matmul() per token -- outputs are bit-identical to the reference's. xq [T][n],
+ * xs [T][n/64], out [T][d]; dots (optional) receives the exact int32 group dots [T][d][n/64];
+ * reps >= 1 runs of the kernel, *ms (optional) = best device time of one run. */
+int qwen_cuda_matmul_batch(float* out, int32_t* dots, const int8_t* xq, const float* xs, const int8_t* wq,
+                           const float* ws, int n, int d, int T, int reps, float* ms);
 int qwen_cuda_rmsnorm(float* out, const float* x, const float* w, int size);                /* forward.c:12-28 */
 int qwen_cuda_softmax(float* x, int size);                                                  /* forward.c:34-77 */
 /* cos/sin: head_dim/2 host-computed values for this position (forward.c:109-110). */

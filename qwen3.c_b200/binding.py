@@ -106,6 +106,8 @@ class QwenLib:
         L.qwen_cuda_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
         L.qwen_cuda_matmul_group_dots.argtypes = [c_int32_p, c_int8_p, c_int8_p, C.c_int, C.c_int, C.c_int]
         L.qwen_cuda_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p]
+        L.qwen_cuda_matmul_batch.argtypes = [c_float_p, c_int32_p, c_int8_p, c_float_p, c_int8_p, c_float_p, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, c_float_p]
 
     def err(self) -> str:
         return (self.lib.qwen_cuda_last_error() or b"").decode()
@@ -148,6 +150,16 @@ class QwenLib:
         self._ok(self.lib.qwen_cuda_matmul_group_dots(dots.ctypes.data_as(c_int32_p), _i8(xq), _i8(wq), n, d, gs),
                  "group_dots")
         return dots.reshape(d, n // gs)
+
+    def matmul_batch(self, xq, xs, wq, ws, n, d, T, want_dots=False, reps=1):
+        """T-token matmul on the tcgen05 tensor cores (prefill). Returns (out[T][d], dots or None, best ms)."""
+        out = np.full((T, d), np.nan, np.float32)
+        dots = np.zeros((T, d, n // 64), np.int32) if want_dots else None
+        ms = C.c_float(0)
+        self._ok(self.lib.qwen_cuda_matmul_batch(_fp(out), dots.ctypes.data_as(c_int32_p) if want_dots else None,
+                                                 _i8(np.ascontiguousarray(xq)), _fp(np.ascontiguousarray(xs)), _i8(wq), _fp(ws),
+                                                 n, d, T, reps, C.byref(ms)), "matmul_batch")
+        return out, dots, ms.value
 
     def rmsnorm(self, x, w):
         x = np.ascontiguousarray(x, np.float32)

@@ -1,0 +1,409 @@
+// prefill_gemm.cu -- Q8_0 group-scaled GEMM for prompt prefill on the 5th-gen tensor cores.
+//
+//   out[t][i] = sum over groups g of ((float) dot_g[t][i] * ws[i][g]) * xs[t][g]
+//   dot_g[t][i] = exact int32 dot of the 64 int8 codes of group g          (reference forward.c:79-101,
+//                                                                            applied to T tokens at once)
+//
+// The reference has no prefill: it runs forward() once per prompt token (completion.c:57-66). This
+// kernel computes the same matmul for T tokens in one pass, with the reference's arithmetic: the
+// int32 group dot is exact (tcgen05.mma kind::i8, s8 x s8 -> s32), each group's term is formed as
+// ((float) dot * ws) * xs and the terms are folded into an fp32 accumulator left to right in group
+// order -- so every output is BIT-IDENTICAL to the reference matmul of that token.
+//
+// Structure (one CTA per 128 weight rows x 128 tokens tile, warp specialised):
+//   warp 0  : TMA producer. Per group: a 128-row x 64-byte box of W straight out of the SG layout
+//             (cp.async.bulk.tensor.2d, SWIZZLE_64B), the matching 128-token x 64-byte box of the
+//             int8 activations, and the 128 activation scales of the group (bulk copy).
+//   warp 1  : MMA issuer (one elected lane): 2 x tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128,
+//             K=32) per group into one of two TMEM accumulator buffers, tcgen05.commit to mbarriers.
+//   warps 2-9: epilogue. tcgen05.ld the group's 128x128 int32 tile (warp w reads TMEM lanes
+//             32*(w%4).., columns 64*(w/4)..), scale-promote to fp32 in registers, release the TMEM
+//             buffer; after the last group store out[t][i].
+// Because the scales change every 64 k-elements on both operands the accumulator must leave TMEM
+// every 2 MMAs: the CUDA-core promotion (4 ops per MAC-column), not the tensor pipe, is the ceiling
+// (SURVEY.md H4). Block-scaled MMA kinds do not apply (UE8M0 / E4M3 scale formats only).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;   // weight rows per tile  (UMMA M, TMEM lanes)
+constexpr int kTileN = 128;   // tokens per tile       (UMMA N, TMEM columns)
+constexpr int kStages = 6;
+constexpr int kABytes = kTileM * 64, kBBytes = kTileN * 64, kSBytes = kTileN * 4;
+constexpr int kStageBytes = kABytes + kBBytes + 1024; // scales padded to keep stages 1024-aligned
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsG = 32 * (2 + kEpiWarps);
+constexpr unsigned long long kTimeoutNsG = 2000000000ull;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long g_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mb_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mb_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a wrong descriptor must not hang the GPU
+__device__ __forceinline__ bool mb_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    if (mb_try(bar, parity)) return true;
+    unsigned long long t0 = 0;
+    for (unsigned spin = 1;; ++spin) {
+        if (mb_try(bar, parity)) return true;
+        if ((spin & 255u) == 0) {
+            if (*(volatile int*) err) return false;
+            const unsigned long long now = g_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kTimeoutNsG) {
+                atomicExch(err, code);
+                return false;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// K-major, SWIZZLE_64B shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) = 512 B between
+// 8-row groups | version 1 [46,48) | layout type 4 = SWIZZLE_64B [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    return (uint64_t) ((saddr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor): D = s32 (2 @ bit 4), A,B = signed 8 bit
+// (1 @ bits 7 and 10), both K-major, N>>3 @ bit 17, M>>4 @ bit 24
+__device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+struct GemmParams {
+    const uint8_t* w;      // SG layout, rows x n
+    const float* xsT;      // [groups][Tpad] activation scales, transposed
+    float* out;            // [T][d]
+    int32_t* dots;         // optional [T][d][groups] exact int32 group dots (test hook)
+    int d, n, T, Tpad;
+    int* err;
+};
+
+__global__ void __launch_bounds__(kThreadsG, 1)
+k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_64B operands want their 512-byte atoms aligned; do not rely on where static shared ends
+    uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 4];
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kTileM, t0 = blockIdx.y * kTileN;
+    const int groups = p.n / 64;
+    const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kStages]);
+    const uint32_t tfull0 = s_u32(&bars[2 * kStages]), tempty0 = s_u32(&bars[2 * kStages + 2]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mb_init(full0 + 8 * s, 1);
+            mb_init(empty0 + 8 * s, 1 + kEpiWarps); // MMA retire + every epilogue warp done with the stage's scales
+        }
+        for (int b = 0; b < 2; ++b) {
+            mb_init(tfull0 + 8 * b, 1);
+            mb_init(tempty0 + 8 * b, kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) { // TMEM: 2 accumulator buffers x 128 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(256)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int g = 0; g < groups; ++g) {
+                const int s = g % kStages;
+                const uint32_t par = (g / kStages) & 1;
+                if (!mb_wait(empty0 + 8 * s, par ^ 1, p.err, 1)) break;
+                const uint32_t base = s_u32(smem + (size_t) s * kStageBytes);
+                mb_expect(full0 + 8 * s, kABytes + kBBytes + kSBytes);
+                tma_2d(base, &map_w, (g >> 2) * QW_SG_BYTES + (g & 3) * 64, row0, full0 + 8 * s);
+                tma_2d(base + kABytes, &map_x, g * 64, t0, full0 + 8 * s);
+                bulk_1d(base + kABytes + kBBytes, p.xsT + (size_t) g * p.Tpad + t0, kSBytes, full0 + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_i8(kTileM, kTileN);
+            for (int g = 0; g < groups; ++g) {
+                const int s = g % kStages, b = g & 1;
+                if (!mb_wait(tempty0 + 8 * b, ((g >> 1) & 1) ^ 1, p.err, 2)) break; // epilogue drained this buffer
+                if (!mb_wait(full0 + 8 * s, (g / kStages) & 1, p.err, 3)) break;    // operands landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = s_u32(smem + (size_t) s * kStageBytes);
+                const uint32_t d = tmem_base + b * kTileN;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) // 64 codes = 2 x K32; the k-th 32-byte slice of every swizzled row
+                    umma_i8(d, umma_desc_sw64(base + 32 * k), umma_desc_sw64(base + kABytes + 32 * k), idesc, k);
+                umma_commit(empty0 + 8 * s);  // smem stage reusable once these MMAs retire
+                umma_commit(tfull0 + 8 * b);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: scale-promote per group
+        const int ew = warp - 2;
+        // a warp may only touch TMEM lanes 32*(warp_id % 4) .. +31 (hardware rule, CTA warp id): warps 2..5
+        // take columns 0..63, warps 6..9 columns 64..127, and inside each set warp%4 picks the lane quarter
+        const int lane_blk = warp & 3, col_blk = ew >> 2;
+        const int i = row0 + lane_blk * 32 + lane;          // weight row of this thread
+        const bool row_ok = i < p.d;
+        const uint8_t* wrow = p.w + (size_t) (row_ok ? i : 0) * qw_row_bytes(p.n);
+        float acc[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
+        bool ok = true;
+        for (int g = 0; g < groups && ok; ++g) {
+            const int s = g % kStages, b = g & 1;
+            const float wsc = row_ok ? __ldg(reinterpret_cast<const float*>(wrow + (g >> 2) * QW_SG_BYTES + 256 + (g & 3) * 4)) : 0.0f;
+            ok = mb_wait(tfull0 + 8 * b, (g >> 1) & 1, p.err, 4);
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float* xs = reinterpret_cast<const float*>(smem + (size_t) s * kStageBytes + kABytes + kBBytes) + col_blk * 64;
+            const uint32_t taddr = tmem_base + ((uint32_t) (lane_blk * 32) << 16) + b * kTileN + col_blk * 64;
+            int v0[32], v1[32];
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32, v1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mb_arrive(tempty0 + 8 * b); // accumulator buffer may be overwritten
+            if (p.dots && row_ok) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    const int t = t0 + col_blk * 64 + c;
+                    if (t < p.T) p.dots[((size_t) t * p.d + i) * groups + g] = c < 32 ? v0[c] : v1[c - 32];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = __fadd_rn(acc[c], q8_term(v0[c], wsc, xs[c]));
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[32 + c] = __fadd_rn(acc[32 + c], q8_term(v1[c], wsc, xs[32 + c]));
+            __syncwarp();
+            if (lane == 0) mb_arrive(empty0 + 8 * s); // done with this stage's activation scales
+        }
+        if (ok && row_ok) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                const int t = t0 + col_blk * 64 + c;
+                if (t < p.T) p.out[(size_t) t * p.d + i] = acc[c];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiled encode_fn() {
+    static EncodeTiled fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiled) f;
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* m, const void* base, uint64_t row_bytes, uint64_t rows, uint32_t box_rows) {
+    EncodeTiled enc = encode_fn();
+    if (!enc) {
+        qw_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return -1;
+    }
+    const cuuint64_t dims[2] = {row_bytes, rows};
+    const cuuint64_t strides[1] = {row_bytes};
+    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        qw_set_error("cuTensorMapEncodeTiled failed (%d) for %llu x %llu", (int) rc, (unsigned long long) row_bytes,
+                     (unsigned long long) rows);
+        return -1;
+    }
+    return 0;
+}
+
+} // namespace
+
+// Device-side entry: W in SG layout (d rows, n columns), xq [T][n] int8 (n % 64 == 0, row pitch n, 16-byte
+// aligned), xsT [n/64][Tpad] fp32, out [T][d]. dots may be NULL. Asynchronous on `st`; *err_dev must be 0.
+int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float* out, int32_t* dots, int d, int n, int T,
+                    int Tpad, int* err_dev, cudaStream_t st, float* ms_out) {
+    if (n % 64 || n % 16 || T <= 0 || d <= 0) {
+        qw_set_error("prefill gemm: bad shape d=%d n=%d T=%d", d, n, T);
+        return -2;
+    }
+    CUtensorMap mw, mx;
+    if (make_map(&mw, w, qw_row_bytes(n), (uint64_t) d, kTileM) || make_map(&mx, xq, (uint64_t) n, (uint64_t) T, kTileN)) return -1;
+    static bool attr = false;
+    const size_t smem = (size_t) kStages * kStageBytes + 1024;
+    if (!attr) {
+        QW_CUDA(cudaFuncSetAttribute(k_prefill_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr = true;
+    }
+    GemmParams p{w, xsT, out, dots, d, n, T, Tpad, err_dev};
+    const dim3 grid((d + kTileM - 1) / kTileM, (T + kTileN - 1) / kTileN);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms_out) {
+        QW_CUDA(cudaEventCreate(&e0));
+        QW_CUDA(cudaEventCreate(&e1));
+        QW_CUDA(cudaEventRecord(e0, st));
+    }
+    k_prefill_gemm<<<grid, kThreadsG, smem, st>>>(mw, mx, p);
+    QW_CUDA(cudaGetLastError());
+    if (ms_out) {
+        QW_CUDA(cudaEventRecord(e1, st));
+        QW_CUDA(cudaEventSynchronize(e1));
+        QW_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return 0;
+}
+
+// Host-in / host-out wrapper: the batched form of matmul() (reference forward.c:79-101 for T tokens).
+// xq [T][n], xs [T][n/64], wq [d][n], ws [d][n/64] in checkpoint layout; out [T][d]; dots optional
+// [T][d][n/64]. reps > 1 re-runs the kernel for timing; *ms (optional) = best device time of one run.
+extern "C" int qwen_cuda_matmul_batch(float* out, int32_t* dots, const int8_t* xq, const float* xs, const int8_t* wq,
+                                      const float* ws, int n, int d, int T, int reps, float* ms) {
+    if (qwen_cuda_device_count() <= 0) {
+        qw_set_error("no CUDA device: this library has no CPU path");
+        return -1;
+    }
+    if (n <= 0 || n % 64 || d <= 0 || T <= 0) {
+        qw_set_error("matmul_batch: n must be a positive multiple of 64");
+        return -2;
+    }
+    const int groups = n / 64, Tpad = (T + kTileN - 1) / kTileN * kTileN;
+    int8_t *dwq = nullptr, *dxq = nullptr;
+    float *dws = nullptr, *dxsT = nullptr, *dout = nullptr;
+    uint8_t* dw = nullptr;
+    int32_t* ddots = nullptr;
+    int* derr = nullptr;
+    int rc = -1;
+    float* xsT = (float*) calloc((size_t) groups * Tpad, sizeof(float));
+    for (int t = 0; t < T && xsT; ++t)
+        for (int g = 0; g < groups; ++g) xsT[(size_t) g * Tpad + t] = xs[(size_t) t * groups + g];
+    do {
+        if (!xsT) break;
+        if (cudaMalloc(&dwq, (size_t) d * n) || cudaMalloc(&dws, (size_t) d * groups * 4) || cudaMalloc(&dw, qw_row_bytes(n) * d)
+            || cudaMalloc(&dxq, (size_t) Tpad * n) || cudaMalloc(&dxsT, (size_t) groups * Tpad * 4)
+            || cudaMalloc(&dout, (size_t) T * d * 4) || cudaMalloc(&derr, 4)
+            || (dots && cudaMalloc(&ddots, (size_t) T * d * groups * 4))) {
+            qw_set_error("matmul_batch: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaMemset(derr, 0, 4);
+        cudaMemset(dxq, 0, (size_t) Tpad * n);
+        cudaMemcpy(dwq, wq, (size_t) d * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(dws, ws, (size_t) d * groups * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dxq, xq, (size_t) T * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(dxsT, xsT, (size_t) groups * Tpad * 4, cudaMemcpyHostToDevice);
+        launch_repack(dwq, dws, n, 0, n, d, dw, 0, 1, 0);
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            qw_set_error("matmul_batch: repack failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        float best = 1e30f;
+        bool bad = false;
+        for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
+            float t = 0;
+            if (qw_prefill_gemm(dw, dxq, dxsT, dout, r == 0 ? ddots : nullptr, d, n, T, Tpad, derr, 0, &t)) {
+                bad = true;
+                break;
+            }
+            if (t < best) best = t;
+        }
+        if (bad) break;
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            qw_set_error("matmul_batch: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        int herr = 0;
+        cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost);
+        if (herr) {
+            qw_set_error("matmul_batch: pipeline wait %d timed out (descriptor / barrier bug)", herr);
+            break;
+        }
+        cudaMemcpy(out, dout, (size_t) T * d * 4, cudaMemcpyDeviceToHost);
+        if (dots) cudaMemcpy(dots, ddots, (size_t) T * d * groups * 4, cudaMemcpyDeviceToHost);
+        if (ms) *ms = best;
+        rc = 0;
+    } while (0);
+    free(xsT);
+    cudaFree(dwq); cudaFree(dws); cudaFree(dw); cudaFree(dxq); cudaFree(dxsT); cudaFree(dout); cudaFree(derr); cudaFree(ddots);
+    return rc;
+}

@@ -375,3 +375,29 @@ def test_quantize_fast_path_bit_exact_on_many_values(qlib, oracle):
     oq, os_ = oracle.q8_quantize(x)
     same(s, os_)
     same(q, oq)
+
+
+@pytest.mark.parametrize("n,d,T", [(64, 8, 1), (320, 300, 200), (2560, 384, 256), (1024, 128, 130)])
+def test_prefill_matmul_batch_bit_identical_to_reference_matmul(qlib, oracle, n, d, T):
+    """The tcgen05 (kind::i8) group-scaled GEMM computes T tokens at once with the reference's own
+    arithmetic: exact int32 group dots, ((float) dot * ws) * xs, fp32 fold in group order. Every
+    output must equal the oracle's per-token matmul BIT FOR BIT; ragged T and d exercise the TMA
+    out-of-bounds fill."""
+    rng = np.random.default_rng(n + d + T)
+    xq = rng.integers(-127, 128, size=(T, n), dtype=np.int8)
+    xs = rng.uniform(1e-3, 1e-1, size=(T, n // 64)).astype(np.float32)
+    wq = rng.integers(-127, 128, size=d * n, dtype=np.int8)
+    ws = rng.uniform(1e-4, 1e-2, size=d * n // 64).astype(np.float32)
+    xq[0, :64] = 127
+    wq[:64] = -127  # extreme group
+    out, dots, _ = qlib.matmul_batch(xq, xs, wq, ws, n, d, T, want_dots=True)
+    for t in (0, T // 2, T - 1):
+        same(dots[t], oracle.group_dots(xq[t], wq, n, d))
+        same(out[t], oracle.matmul(xq[t], xs[t], wq, ws, n, d))
+    assert dots[0, 0, 0] == -64 * 127 * 127
+    # all tokens, cheaply: the fold is reproducible from the integer dots alone
+    acc = np.zeros((T, d), np.float32)
+    w2 = ws.reshape(d, -1)
+    for g in range(n // 64):
+        acc = acc + (dots[:, :, g].astype(np.float32) * w2[None, :, g]) * xs[:, None, g]
+    same(out, acc)
