@@ -240,6 +240,8 @@ extern "C" void qwen_cuda_host_free(void* p) {
 int qw_mega_profile_enable(QwenCudaCtx* c);
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems);
 int qw_mega_tlog(QwenCudaCtx* c, int warp, unsigned long long* host);
+int qw_mega_reset(QwenCudaCtx* c);
+const float* qw_mega_debug_ptr(QwenCudaCtx* c, const char* what);
 extern "C" int qwen_cuda_debug_tile_log(QwenCudaCtx* c, int warp, unsigned long long* host) { return c ? qw_mega_tlog(c, warp, host) : -2; }
 extern "C" int qwen_cuda_debug_profile_enable(QwenCudaCtx* c) { return c ? qw_mega_profile_enable(c) : -2; }
 extern "C" int qwen_cuda_debug_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
@@ -277,10 +279,9 @@ static int step(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
 static int qw_check_flag(QwenCudaCtx* c) {
     const int flag = *(volatile int*) c->err_flag;
     if (flag) {
-        qw_set_error("decode kernel reported error %d (grid barrier timeout)", flag);
+        qw_set_error("decode kernel reported error %d (a wait inside the persistent kernel timed out)", flag);
         *c->err_flag = 0;
-        cudaMemset(c->bar_counter, 0, 512 * 8); // the grid-barrier flags are meaningless after an abort
-        c->bar_epoch = 0;
+        qw_mega_reset(c); // the flow arenas are meaningless after an abort
         return -3;
     }
     return 0;
@@ -396,6 +397,8 @@ extern "C" int qwen_cuda_debug_read(QwenCudaCtx* c, const char* what, void* host
     if (bytes > max_bytes) bytes = max_bytes;
     QW_CUDA(cudaSetDevice(c->device));
     QW_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->path == 0) // the persistent kernel keeps x / h / qkv of every layer in its flow arena
+        if (const float* f = qw_mega_debug_ptr(c, what)) src = f;
     QW_CUDA(cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost));
     return (int) elems;
 }

@@ -1,87 +1,97 @@
 // decode_mega.cu -- the whole decode step (reference src/forward.c:225-350) as ONE
-// persistent cooperative sm_100a kernel.
+// persistent sm_100a kernel, one CTA per SM, organised as a DATAFLOW: there is no grid barrier.
 //
 // Why one kernel: at batch 1 every op is a matrix-vector product whose only cost is
 // streaming its weights from HBM once. A layer is ~107 MB (Qwen3-4B) = ~16 us of HBM
 // time split over 7 dependent GEMVs; a launch-per-op design spends about as long in
-// launch gaps and pipeline fill/drain as it does streaming. Here one CTA per SM stays
-// resident for the whole token:
+// launch gaps and pipeline fill/drain as it does streaming.
 //
-//   * warp 16 (one elected lane) is the PRODUCER. It walks the step's fixed schedule of
+//   * warp 15 (one elected lane) is the PRODUCER. It walks the step's fixed schedule of
 //     weight tiles and KV-cache chunks and copies each into a shared-memory ring with
 //     cp.async.bulk (TMA bulk copy, completion on an mbarrier). It never waits for
-//     activations, so it runs up to one ring (6-7 x 28 KB per SM, ~29 MB chip-wide)
-//     AHEAD of the math, straight through phase boundaries and grid barriers. HBM
-//     stays busy while the consumers synchronise.
-//   * warps 0..15 are CONSUMERS. Per phase they build the quantised activation vector
-//     in shared memory (RMSNorm + Q8_0 quantise, fused), then eat tiles from the ring:
-//     a half-warp takes one 272-byte super-group record, 4 x dp4a per lane, int32 group
-//     dots by shuffle, fp32 scaling exactly as the reference does, and one thread per
-//     row folds the group terms left to right -- the reference's own order, so a GEMV
-//     is bit-identical to the reference for identical inputs.
-//   * phases are separated by a grid-wide barrier (one atomic + spin per CTA).
+//     activations, so it runs up to one ring (7 x 28 KB per SM, ~29 MB chip-wide) AHEAD
+//     of the math, straight through phase boundaries. HBM stays busy while the consumers
+//     wait for each other's results.
+//   * warps 0..14 are CONSUMERS. Per phase they build the quantised activation vector in
+//     shared memory (RMSNorm + Q8_0 quantise, fused), then eat tiles from the ring.
+//   * Phases hand vectors to each other through a FLOW ARENA in global memory (L2): every
+//     word of the arena starts as a sentinel bit pattern that no computation can produce
+//     (a signalling NaN whose low bytes are the int8 code -128, which the quantiser never
+//     emits). A producer simply stores its result; a consumer polls the words it needs with
+//     ld.relaxed.gpu until none is the sentinel. No flags, no fences, no counters: one store
+//     latency plus one L2 round trip per hand-off, and a CTA starts a phase the moment ITS
+//     inputs exist. Every (layer, vector) has its own slot in the arena, so each word is
+//     written exactly once per launch and there is no write-after-read hazard inside a launch;
+//     two arenas alternate between launches and each launch refills the other one with the
+//     sentinel for the next launch (stream order makes that refill complete before it is used).
 //
 // Work split: every matrix is split by contiguous row ranges over the CTAs (no split-K,
-// no atomics -> deterministic). Attention is split-KV over (kv head, 28-position chunk)
-// units with an online-softmax merge in a small combine phase.
+// no atomics -> deterministic, bit-identical run to run). Attention is split-KV: the
+// (kv head, 28-position chunk) tiles are spread evenly over all CTAs, each warp runs a whole
+// online-softmax over its share of the positions with no cross-warp synchronisation, the CTA merges its
+// 15 warp states in shared memory and publishes one partial per head; (head, half) combine tasks
+// merge the partials of a head and write the attention output already quantised for wo.
 //
 // Every wait in this file has a wall-clock timeout that raises a sticky error flag
 // instead of hanging the GPU.
-#include <cooperative_groups.h>
-
 #include <stdlib.h>
 
 #include <algorithm>
 
 #include "common.cuh"
 
-#ifndef QW_GEMV_PRED
-#define QW_GEMV_PRED 0
-#endif
-
 namespace {
 
-constexpr int kConsumerWarps = 16;
+constexpr int kConsumerWarps = 15;         // + the producer warp = 16 warps = 512 threads: 128 registers per thread
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;
 constexpr int kSlotBytes = 28672;           // one ring slot: 105 SG records or 2 x 28 KV rows
-constexpr int kChunk = 28;                  // KV positions per attention unit (2*28*512 B = one slot)
+constexpr int kChunk = 28;                  // KV positions per attention tile (2*28*512 B = one slot)
 constexpr int kMaxSlots = 8;
 constexpr int kMaxGrid = 256;
-constexpr unsigned long long kTimeoutNs = 4000000000ull;
-constexpr int kTileLog = 8192;
-constexpr int kProfSlots = 16; // per layer: stamps after each phase step (CTA-local, thread 0)
+constexpr unsigned long long kTimeoutNs = 2000000000ull;
+constexpr int kProfSlots = 16;              // per layer: stamps after each phase step (CTA-local, thread 0)
+constexpr uint32_t kSent = 0x7F808080u;     // "not written yet": sNaN as fp32, contains code -128 as int8x4
+constexpr int kPartStride = 132;            // floats per published attention partial: acc[128], m, l, pad
+
+// one weight matrix of the step's schedule, filled on the host (no divisions left for the kernel)
+struct MatDesc {
+    const uint8_t* base; // layer 0
+    size_t stride;       // bytes between layers
+    int rows, n, gran;   // rows, columns, granularity of the per-CTA row split
+    int rt;              // rows per ring tile
+    int kind;            // epilogue: 0 out[row] = v, 1 out[row] = resid[row] + v, 2 out[row/2] = silu(v0) * v1
+};
 
 struct MegaParams {
     int D, Hdl, L, Hl, KVHl, Pl, Kl, Vl, S, kv_mul;
     int pos, token, layers_run;
-    int perm; // CTA -> row-block permutation multiplier (coprime to the grid)
-    int copy_split; // debug: issue each tile as this many bulk copies
-    int dbg_mode; // 0 normal; 1 consumers skip the GEMV math (ring throughput test); 2 skip attention math too
+    int perm;       // CTA -> row-block permutation multiplier (coprime to the grid)
+    int dbg_mode;   // 0 normal; 1 consumers skip the GEMV math (ring throughput test)
     const int* token_dev;
-    const uint8_t *w_qkv, *w_o, *w_13, *w_2, *w_cls, *w_emb;
-    size_t s_qkv, s_o, s_13, s_2;
+    MatDesc mat[5]; // 0 wq|wk|wv, 1 wo, 2 w1/w3 interleaved, 3 w2, 4 classifier
+    const uint8_t* w_emb;
     const float *att_norm, *ffn_norm, *out_norm, *q_norm, *k_norm, *rope_cos, *rope_sin;
     float *k_cache, *v_cache;
-    float *x, *qkv, *att, *h, *logits;
-    uint8_t* att_q; // attention output, quantised, SG layout (row of Pl columns)
-    float *part_m, *part_l, *part_acc;
-    unsigned long long* bar;
-    unsigned long long bar_base;
+    float* flow;        // this launch's arena: every word is kSent until its producer stores it
+    float* flow_other;  // the other arena: refilled with kSent by this launch, used by the next
+    float* flow_x0;     // [D] inside `flow`: the dequantised embedding row (residual stream entering layer 0)
+    size_t flow_layer_words, flow_words;
+    int o_xa, o_xb, o_qkv, o_h, o_attq, o_part, part_slots; // word offsets inside a layer's block
+    float *att, *logits;
     int* err;
-    unsigned long long* tlog; // optional [4][kTileLog] per-tile stamps of CTA 0 (debug)
-    int tlog_warp;
-    unsigned long long* prof; // optional [CTA][kProfSlots] globaltimer stamps (debug)
+    unsigned long long* prof; // optional [CTA][L+1][kProfSlots] globaltimer stamps (debug)
     int nslot, off_xq, off_scr, off_misc, off_bar;
 };
 
 struct MegaState {
-    uint8_t* att_q = nullptr;
-    float *part_m = nullptr, *part_l = nullptr, *part_acc = nullptr;
-    int grid = 0, nslot = 0, dbg_mode = 0, copy_split = 1, perm = 1;
+    float* arena[2] = {nullptr, nullptr};
+    size_t layer_words = 0, words = 0, x0_off = 0;
+    int o_xa = 0, o_xb = 0, o_qkv = 0, o_h = 0, o_attq = 0, o_part = 0, part_slots = 0;
+    unsigned launches = 0;
+    int last_layers = 0;
+    int grid = 0, nslot = 0, dbg_mode = 0, perm = 1;
     unsigned long long* prof = nullptr;
-    unsigned long long* tlog = nullptr;
-    int tlog_warp = 0;
     size_t smem = 0;
     int off_xq, off_scr, off_misc, off_bar;
 };
@@ -120,14 +130,28 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
     return t;
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+
+// flow arena accesses: always at L2 (gpu scope), never cached in L1
+__device__ __forceinline__ uint32_t ldf_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ uint4 ldf_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void stf_f32(float* p, float v) {
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stf_u32(void* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stf_f4(float* p, const float4& v) {
+    asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ bool unset4(const uint4& v) { return v.x == kSent || v.y == kSent || v.z == kSent || v.w == kSent; }
 
 struct Shared {
     uint8_t* ring;
@@ -138,147 +162,158 @@ struct Shared {
     volatile int* abort_flag;
 };
 
-__device__ __forceinline__ void mbar_wait(const Shared& sh, const MegaParams& p, uint32_t bar, uint32_t parity, int code) {
-    if (mbar_try_wait(bar, parity)) return;
+// Slow paths are deliberately NOT inlined: the kernel's code must stay small enough for the SM's
+// instruction cache (an earlier build inlined the timeout logic at ~40 sites: 577 KB of SASS, every
+// phase change ran cold code fetched through a saturated L2).
+__device__ __noinline__ void mbar_wait_slow(volatile int* abort_flag, int* err, uint32_t bar, uint32_t parity, int code) {
     unsigned long long t0 = 0;
-    for (unsigned spin = 1;; ++spin) {
-        if (mbar_try_wait(bar, parity)) return;
-        if ((spin & 255u) == 0) { // look at the clock only now and then: the common case is a short wait
-            if (*sh.abort_flag) return;
+    for (unsigned n = 1; !mbar_try_wait(bar, parity); ++n) {
+        if ((n & 255u) == 0) {
+            if (*abort_flag) return;
             const unsigned long long now = gtime_ns();
             if (t0 == 0) t0 = now;
             if (now - t0 > kTimeoutNs) {
-                *sh.abort_flag = code;
-                *p.err = code;
+                *abort_flag = code;
+                *err = code;
                 return;
             }
         }
     }
 }
-
-// Grid-wide barrier among the consumer threads of every CTA: bar.sync orders the CTA's writes
-// before thread 0's release-add on one global counter; thread 0 polls it with ld.acquire and a
-// second bar.sync hands the other CTAs' writes to every thread here (readers use ld.cg /
-// ld.acquire afterwards, never L1). ~1.5 us on 148 CTAs, all of it L2 round trips. A variant
-// with one flag word per CTA and 148 polling threads per CTA was measured and is 3x SLOWER
-// (148 x 5 polled lines hot-spot the L2 slices), so the single counter stays.
-__device__ __forceinline__ void grid_barrier(const Shared& sh, const MegaParams& p, int& nbar) {
-    bar_consumers();
-    if (threadIdx.x == 0) {
-        const unsigned long long target = p.bar_base + (unsigned long long) (nbar + 1) * gridDim.x;
-        red_release_add_u64(p.bar, 1ull);
-        unsigned long long t0 = 0;
-        for (unsigned spin = 1; ld_acquire_u64(p.bar) < target; ++spin) {
-            if ((spin & 1023u) == 0) {
-                const unsigned long long now = gtime_ns();
-                if (t0 == 0) t0 = now;
-                if (*sh.abort_flag || now - t0 > kTimeoutNs) {
-                    *sh.abort_flag = 100 + nbar;
-                    *p.err = 100 + nbar;
-                    break;
-                }
+__device__ __forceinline__ void mbar_wait(const Shared& sh, const MegaParams& p, uint32_t bar, uint32_t parity, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(sh.abort_flag, p.err, bar, parity, code);
+}
+// poll until the 4 (or 1) words at q are all written
+__device__ __noinline__ uint4 poll4_slow(volatile int* abort_flag, int* err, const void* q, int code) {
+    unsigned long long t0 = 0;
+    uint4 v = ldf_u4(q);
+    for (unsigned n = 1; unset4(v); ++n) {
+        if ((n & 255u) == 0) {
+            if (*abort_flag) break;
+            const unsigned long long now = gtime_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kTimeoutNs) {
+                *abort_flag = code;
+                *err = code;
+                break;
             }
         }
+        v = ldf_u4(q);
     }
-    bar_consumers();
-    ++nbar;
+    return v;
 }
+__device__ __noinline__ uint32_t poll1_slow(volatile int* abort_flag, int* err, const void* q, int code) {
+    unsigned long long t0 = 0;
+    uint32_t v = ldf_u32(q);
+    for (unsigned n = 1; v == kSent; ++n) {
+        if ((n & 255u) == 0) {
+            if (*abort_flag) break;
+            const unsigned long long now = gtime_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kTimeoutNs) {
+                *abort_flag = code;
+                *err = code;
+                break;
+            }
+        }
+        v = ldf_u32(q);
+    }
+    return v;
+}
+__device__ __forceinline__ uint4 poll4(const Shared& sh, const MegaParams& p, const void* q, int code) {
+    return poll4_slow(sh.abort_flag, p.err, q, code);
+}
+__device__ __forceinline__ float poll1(const Shared& sh, const MegaParams& p, const float* q, int code) {
+    const uint32_t v = ldf_u32(q);
+    return __uint_as_float(v != kSent ? v : poll1_slow(sh.abort_flag, p.err, q, code));
+}
+__device__ __forceinline__ float4 as_f4(const uint4& v) {
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+__device__ __forceinline__ float* flow_layer(const MegaParams& p, int l) { return p.flow + (size_t) l * p.flow_layer_words; }
 
 // ---------------------------------------------------------------- schedule (shared by producer and consumers)
-struct MatPhase {
-    const uint8_t* base;
-    int rows, n, gran;
-    int perm = 1;
-};
-__device__ __forceinline__ void cta_rows(const MatPhase& m, int& r0, int& r1) {
-    const long long units = m.rows / m.gran;
+// The step is a fixed list of phases: 4 per layer (QKV, WO, W1/W3, W2) and the classifier. Producer and
+// consumers walk it with ONE copy of each routine (runtime descriptors, no per-phase template
+// instances): the whole kernel has to fit the SM's 32 KB instruction cache or every phase change
+// fetches cold code through an L2 that is busy streaming weights.
+__device__ __forceinline__ int my_block(int perm) { return (int) ((blockIdx.x * (unsigned) perm) % gridDim.x); }
+__device__ __forceinline__ void cta_rows(const MatDesc& m, int perm, int& r0, int& r1) {
+    const unsigned units = (unsigned) m.rows / (unsigned) m.gran; // units * grid < 2^31 for every supported shape
     // CTA -> row-block map: a multiplicative permutation (perm coprime to the grid). With the identity
-    // map the GEMV phases ran 8-10 % slower and a fixed third of the CTAs arrived 2-4 us late at every
-    // barrier (measured, profiles/r1_k_decode_summary.md); any scattering permutation removes that.
-    const int b = (int) ((blockIdx.x * (unsigned) m.perm) % gridDim.x);
+    // map the GEMV phases ran 8-10 % slower and a fixed third of the CTAs finished 2-4 us late in every
+    // phase (measured, profiles/r1_k_decode_summary.md); any scattering permutation removes that.
+    const unsigned b = (unsigned) my_block(perm);
     r0 = (int) (units * b / gridDim.x) * m.gran;
     r1 = (int) (units * (b + 1) / gridDim.x) * m.gran;
 }
-__device__ __forceinline__ int rows_per_tile(const MatPhase& m) {
-    int rt = kSlotBytes / (int) qw_row_bytes(m.n);
-    if (rt >= 2) rt &= ~1; // whole 2-row units per tile
-    return rt < m.gran ? m.gran : rt;
-}
-__device__ __forceinline__ MatPhase ph_qkv(const MegaParams& p, int l) { return {p.w_qkv + l * p.s_qkv, p.Pl + 2 * p.Kl, p.D, 1, p.perm}; }
-__device__ __forceinline__ MatPhase ph_o(const MegaParams& p, int l) { return {p.w_o + l * p.s_o, p.D, p.Pl, 1, p.perm}; }
-__device__ __forceinline__ MatPhase ph_13(const MegaParams& p, int l) { return {p.w_13 + l * p.s_13, 2 * p.Hdl, p.D, 2, p.perm}; }
-__device__ __forceinline__ MatPhase ph_2(const MegaParams& p, int l) { return {p.w_2 + l * p.s_2, p.D, p.Hdl, 1, p.perm}; }
-__device__ __forceinline__ MatPhase ph_cls(const MegaParams& p) { return {p.w_cls, p.Vl, p.D, 1, p.perm}; }
 
-// index of the unit block this CTA attends over (also the slot of its partial results)
-__device__ __forceinline__ int attn_block(const MegaParams& p) {
-    return (int) ((blockIdx.x * (unsigned) p.perm) % gridDim.x);
-}
+// Attention tiles: unit u = (kv head u / nc, chunk u % nc), U = KVH * nc units, block b owns
+// units [U*b/G, U*(b+1)/G).
 __device__ __forceinline__ void attn_units(const MegaParams& p, int& nc, int& u0, int& u1) {
     nc = p.pos / kChunk + 1;
-    const long long U = (long long) p.KVHl * nc;
-    const int b = attn_block(p);
+    const unsigned U = (unsigned) (p.KVHl * nc); // U * grid < 2^31 (KVH <= 64, S <= 2^17)
+    const unsigned b = (unsigned) my_block(p.perm);
     u0 = (int) (U * b / gridDim.x);
     u1 = (int) (U * (b + 1) / gridDim.x);
 }
-
-// ---------------------------------------------------------------- producer
-__device__ void produce_mat(const Shared& sh, const MegaParams& p, const MatPhase& m, unsigned& it) {
-    int r0, r1;
-    cta_rows(m, r0, r1);
-    const int rt = rows_per_tile(m);
-    const size_t rb = qw_row_bytes(m.n);
-    for (int r = r0; r < r1; r += rt, ++it) {
-        const int nr = min(rt, r1 - r);
-        const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
-        mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 1);
-        const uint32_t bytes = (uint32_t) (nr * rb);
-        if (p.tlog && blockIdx.x == 0 && it < kTileLog) p.tlog[it] = gtime_ns();
-        mbar_expect_tx(sh.full + slot * 8, bytes);
-        const uint32_t dst = smem_u32(sh.ring + (size_t) slot * kSlotBytes);
-        const uint8_t* src = m.base + (size_t) r * rb;
-        const uint32_t piece = ((bytes / p.copy_split) + 15u) & ~15u;
-        for (uint32_t o = 0; o < bytes; o += piece) bulk_g2s(dst + o, src + o, min(piece, bytes - o), sh.full + slot * 8);
-    }
+// the block whose range contains `unit`
+__device__ __noinline__ int block_of_unit(unsigned unit, unsigned U, unsigned G) {
+    unsigned b = unit * G / U;
+    while (b + 1 < G && U * (b + 1) / G <= unit) ++b;
+    while (b > 0 && U * b / G > unit) --b;
+    return (int) b;
 }
 
-__device__ void produce_attn(const Shared& sh, const MegaParams& p, int l, unsigned& it) {
-    int nc, u0, u1;
-    attn_units(p, nc, u0, u1);
-    for (int u = u0; u < u1; ++u, ++it) {
-        const int kvh = u / nc, c = u % nc;
-        const int p0 = c * kChunk;
-        const int cnt = min(p.pos, p0 + kChunk) - p0; // slot `pos` itself is produced by this step
-        const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
-        mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 2);
-        if (p.tlog && blockIdx.x == 0 && it < kTileLog) p.tlog[it] = gtime_ns();
-        if (cnt > 0) {
-            const size_t off = (((size_t) l * p.KVHl + kvh) * p.S + p0) * 128;
-            const uint32_t bytes = (uint32_t) cnt * 512u;
-            const uint32_t dst = smem_u32(sh.ring + (size_t) slot * kSlotBytes);
-            mbar_expect_tx(sh.full + slot * 8, 2 * bytes);
-            bulk_g2s(dst, p.k_cache + off, bytes, sh.full + slot * 8);
-            bulk_g2s(dst + kChunk * 512, p.v_cache + off, bytes, sh.full + slot * 8);
-        } else {
-            mbar_arrive(sh.full + slot * 8);
+// ---------------------------------------------------------------- producer
+__device__ void producer(const Shared& sh, const MegaParams& p) {
+    unsigned it = 0;
+    const int nph = 4 * p.layers_run;
+#pragma unroll 1
+    for (int ph = 0; ph <= nph; ++ph) {
+        const int l = ph >> 2, k = ph == nph ? 4 : (ph & 3);
+        if (k == 1) { // the layer's KV tiles come between QKV and WO
+            int nc, u0, u1;
+            attn_units(p, nc, u0, u1);
+#pragma unroll 1
+            for (int u = u0; u < u1; ++u, ++it) {
+                const int kvh = u / nc, c = u % nc;
+                const int p0 = c * kChunk;
+                const int cnt = min(p.pos, p0 + kChunk) - p0; // slot `pos` itself is produced by this step
+                const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
+                mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 2);
+                if (cnt > 0) {
+                    const size_t off = (((size_t) l * p.KVHl + kvh) * p.S + p0) * 128;
+                    const uint32_t bytes = (uint32_t) cnt * 512u;
+                    const uint32_t dst = smem_u32(sh.ring + (size_t) slot * kSlotBytes);
+                    mbar_expect_tx(sh.full + slot * 8, 2 * bytes);
+                    bulk_g2s(dst, p.k_cache + off, bytes, sh.full + slot * 8);
+                    bulk_g2s(dst + kChunk * 512, p.v_cache + off, bytes, sh.full + slot * 8);
+                } else {
+                    mbar_arrive(sh.full + slot * 8);
+                }
+            }
+        }
+        const MatDesc& m = p.mat[k];
+        int r0, r1;
+        cta_rows(m, p.perm, r0, r1);
+        const size_t rb = qw_row_bytes(m.n);
+        const uint8_t* base = m.base + (size_t) l * m.stride;
+#pragma unroll 1
+        for (int r = r0; r < r1; r += m.rt, ++it) {
+            const int nr = min(m.rt, r1 - r);
+            const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
+            mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 1);
+            const uint32_t bytes = (uint32_t) (nr * rb);
+            mbar_expect_tx(sh.full + slot * 8, bytes);
+            bulk_g2s(smem_u32(sh.ring + (size_t) slot * kSlotBytes), base + (size_t) r * rb, bytes, sh.full + slot * 8);
         }
     }
 }
 
-__device__ void producer(const Shared& sh, const MegaParams& p) {
-    unsigned it = 0;
-    for (int l = 0; l < p.layers_run; ++l) {
-        produce_mat(sh, p, ph_qkv(p, l), it);
-        produce_attn(sh, p, l, it);
-        produce_mat(sh, p, ph_o(p, l), it);
-        produce_mat(sh, p, ph_13(p, l), it);
-        produce_mat(sh, p, ph_2(p, l), it);
-    }
-    produce_mat(sh, p, ph_cls(p), it);
-}
-
 // ---------------------------------------------------------------- consumer: GEMV over ring tiles
-// Work unit = 2 consecutive rows, owned by ONE warp (unit u of the CTA's range -> warp u % 16).
+// Work unit = 2 consecutive rows, owned by ONE warp (unit u of the CTA's range -> warp u % 15).
 // Lane L owns Q8_0 groups L, L+32, ... of both rows: a group is 64 codes = 4 x LDS.128 of W per
 // row and 4 x LDS.128 of x, shared by the two rows (x sits in shared memory in the same record
 // layout, so one offset serves both). dp4a has ~24 cycles of dependent latency on this part
@@ -289,12 +324,13 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
 // added in fp32; lanes are combined by a shuffle tree.
 // No CTA-wide barrier per tile: warps meet only at the ring's mbarriers, so with one unit per
 // tile (n = 9728) different warps work on different ring slots at the same time.
-// KIND 0: out[row] = v      KIND 1: x[row] += v (residual)      KIND 2: h[row/2] = silu(v0) * v1
-template <int KIND>
-__device__ void consume_mat(const Shared& sh, const MegaParams& p, const MatPhase& m, unsigned& it, float* out) {
+// kind 0: out[row] = v      kind 1: out[row] = resid[row] + v      kind 2: out[row/2] = silu(v0) * v1
+// `out` is a flow-arena vector (or the logits): each element is stored exactly once.
+__device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& p, const MatDesc& m, int /*layer*/, unsigned& it, float* out, const float* resid) {
     int r0, r1;
-    cta_rows(m, r0, r1);
-    const int rt = rows_per_tile(m);
+    cta_rows(m, p.perm, r0, r1);
+    const int rt = m.rt;
+    const int KIND = m.kind;
     const int sgpr = qw_sg_per_row(m.n);
     const size_t rb = (size_t) sgpr * QW_SG_BYTES;
     const int groups = sgpr * 4; // padded groups carry zero codes and zero scales: they add +0
@@ -304,20 +340,15 @@ __device__ void consume_mat(const Shared& sh, const MegaParams& p, const MatPhas
     const int upt = (rt + 1) / 2;             // units per tile (rt is 1 only when a row fills the slot)
     const int rows_pu = rt >= 2 ? 2 : 1;      // rows per unit
     const int total = (nrows + rows_pu - 1) / rows_pu;
+#pragma unroll 1
     for (int t0 = 0; t0 < total; t0 += upt, ++it) {
         const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
-#ifdef QW_TLOG
-        const bool logme = p.tlog && blockIdx.x == 0 && warp == p.tlog_warp && lane == 0 && it < kTileLog;
-#else
-        constexpr bool logme = false;
-#endif
-        if (logme) p.tlog[kTileLog + it] = gtime_ns();
         mbar_wait(sh, p, sh.full + slot * 8, par, 3);
-        if (logme) p.tlog[2 * kTileLog + it] = gtime_ns();
         const uint8_t* tile = sh.ring + (size_t) slot * kSlotBytes;
         const int t1 = p.dbg_mode >= 1 ? t0 : min(t0 + upt, total);
         int ufirst = (warp - t0) % kConsumerWarps; // first unit >= t0 owned by this warp (u % 15 == warp)
         if (ufirst < 0) ufirst += kConsumerWarps;
+#pragma unroll 1
         for (int u = t0 + ufirst; u < t1; u += kConsumerWarps) {
             const int lr = (u - t0) * rows_pu;          // first row of the unit inside the tile
             const int grow = r0 + u * rows_pu;          // its global row
@@ -325,45 +356,14 @@ __device__ void consume_mat(const Shared& sh, const MegaParams& p, const MatPhas
             const uint8_t* rowa = tile + (size_t) lr * rb;
             const uint8_t* rowb = two ? rowa + rb : rowa;
             float xres = 0.0f;
-            if (KIND == 1 && lane < 2 && (lane == 0 || two)) xres = __ldcg(out + grow + lane); // hide the L2 round trip
+            if (KIND == 1 && lane < 2 && (lane == 0 || two)) // issued early: hides the L2 round trip
+                xres = __uint_as_float(ldf_u32(resid + grow + lane));
             float acca = 0.0f, accb = 0.0f;
+#pragma unroll 1
             for (int G = lane; G < groups; G += 64) {
                 const int G2 = G + 32;
                 const bool has2 = G2 < groups;
                 const int off = (G >> 2) * QW_SG_BYTES + (G & 3) * 64;
-#if QW_GEMV_PRED
-                const int off2 = (G2 >> 2) * QW_SG_BYTES + (G2 & 3) * 64;
-                int da0 = 0, da1 = 0, db0 = 0, db1 = 0;
-                if (has2) {
-#pragma unroll 2
-                    for (int i = 0; i < 4; ++i) {
-                        const int pc = ((i + rot) & 3) * 16;
-                        const int4 x0 = *reinterpret_cast<const int4*>(sh.xq + off + pc);
-                        const int4 x1 = *reinterpret_cast<const int4*>(sh.xq + off2 + pc);
-                        const int4 a0 = *reinterpret_cast<const int4*>(rowa + off + pc);
-                        const int4 a1 = *reinterpret_cast<const int4*>(rowa + off2 + pc);
-                        const int4 b0 = *reinterpret_cast<const int4*>(rowb + off + pc);
-                        const int4 b1 = *reinterpret_cast<const int4*>(rowb + off2 + pc);
-                        da0 = __dp4a(a0.x, x0.x, da0); da1 = __dp4a(a1.x, x1.x, da1); db0 = __dp4a(b0.x, x0.x, db0); db1 = __dp4a(b1.x, x1.x, db1);
-                        da0 = __dp4a(a0.y, x0.y, da0); da1 = __dp4a(a1.y, x1.y, da1); db0 = __dp4a(b0.y, x0.y, db0); db1 = __dp4a(b1.y, x1.y, db1);
-                        da0 = __dp4a(a0.z, x0.z, da0); da1 = __dp4a(a1.z, x1.z, da1); db0 = __dp4a(b0.z, x0.z, db0); db1 = __dp4a(b1.z, x1.z, db1);
-                        da0 = __dp4a(a0.w, x0.w, da0); da1 = __dp4a(a1.w, x1.w, da1); db0 = __dp4a(b0.w, x0.w, db0); db1 = __dp4a(b1.w, x1.w, db1);
-                    }
-                } else { // lanes without a second group issue no loads for it (a partial warp LDS costs fewer wavefronts)
-                    int dc0 = 0, dc1 = 0; // split each row's chain in two to keep four chains in flight
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int pc = ((i + rot) & 3) * 16;
-                        const int4 x0 = *reinterpret_cast<const int4*>(sh.xq + off + pc);
-                        const int4 a0 = *reinterpret_cast<const int4*>(rowa + off + pc);
-                        const int4 b0 = *reinterpret_cast<const int4*>(rowb + off + pc);
-                        da0 = __dp4a(a0.x, x0.x, da0); dc0 = __dp4a(a0.y, x0.y, dc0); db0 = __dp4a(b0.x, x0.x, db0); dc1 = __dp4a(b0.y, x0.y, dc1);
-                        da0 = __dp4a(a0.z, x0.z, da0); dc0 = __dp4a(a0.w, x0.w, dc0); db0 = __dp4a(b0.z, x0.z, db0); dc1 = __dp4a(b0.w, x0.w, dc1);
-                    }
-                    da0 += dc0;
-                    db0 += dc1;
-                }
-#else
                 const int off2 = has2 ? (G2 >> 2) * QW_SG_BYTES + (G2 & 3) * 64 : off;
                 int da0 = 0, da1 = 0, db0 = 0, db1 = 0;
 #pragma unroll
@@ -380,7 +380,6 @@ __device__ void consume_mat(const Shared& sh, const MegaParams& p, const MatPhas
                     da0 = __dp4a(a0.z, x0.z, da0); da1 = __dp4a(a1.z, x1.z, da1); db0 = __dp4a(b0.z, x0.z, db0); db1 = __dp4a(b1.z, x1.z, db1);
                     da0 = __dp4a(a0.w, x0.w, da0); da1 = __dp4a(a1.w, x1.w, da1); db0 = __dp4a(b0.w, x0.w, db0); db1 = __dp4a(b1.w, x1.w, db1);
                 }
-#endif
                 const int so = (G >> 2) * QW_SG_BYTES + 256 + (G & 3) * 4;
                 const float xs0 = *reinterpret_cast<const float*>(sh.xq + so);
                 acca = __fadd_rn(acca, q8_term(da0, *reinterpret_cast<const float*>(rowa + so), xs0));
@@ -398,468 +397,513 @@ __device__ void consume_mat(const Shared& sh, const MegaParams& p, const MatPhas
                 accb = __fadd_rn(accb, __shfl_xor_sync(0xffffffffu, accb, o));
             }
             if (KIND == 2) {
-                if (lane == 0) out[grow >> 1] = __fmul_rn(silu_ref(acca), accb);
+                if (lane == 0) stf_f32(out + (grow >> 1), __fmul_rn(silu_ref(acca), accb));
             } else if (lane < 2 && (lane == 0 || two)) {
                 const float v = lane == 0 ? acca : accb;
-                out[grow + lane] = KIND == 1 ? __fadd_rn(xres, v) : v;
+                stf_f32(out + grow + lane, KIND == 1 ? __fadd_rn(xres, v) : v);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(sh.empty + slot * 8); // this warp is done with the slot
-        if (logme) p.tlog[3 * kTileLog + it] = gtime_ns();
     }
+    // push this warp's results out NOW: without a fence the stores sit in the SM's write path for
+    // microseconds (measured, scripts/ubench/handoff.cu: 2.7 us per hand-off without, 1.05 us with)
+    __threadfence();
 }
 
 // ---------------------------------------------------------------- consumer: prologues
-// store one quantised group (64 codes + scale) into the shared activation vector (SG layout)
-__device__ __forceinline__ void put_group(uint8_t* xq, int g, int lane, float a, float b) {
-    const float scale = q8_scale(warp_max(fmaxf(fabsf(a), fabsf(b))));
-    int8_t* codes = reinterpret_cast<int8_t*>(xq + (g >> 2) * QW_SG_BYTES + (g & 3) * 64);
-    codes[lane] = (int8_t) q8_code(a, scale);
-    codes[lane + 32] = (int8_t) q8_code(b, scale);
-    if (lane == 0) *reinterpret_cast<float*>(xq + (g >> 2) * QW_SG_BYTES + 256 + (g & 3) * 4) = scale;
-}
-__device__ __forceinline__ void zero_group(uint8_t* xq, int g, int lane) {
-    int8_t* codes = reinterpret_cast<int8_t*>(xq + (g >> 2) * QW_SG_BYTES + (g & 3) * 64);
-    codes[lane] = 0;
-    codes[lane + 32] = 0;
-    if (lane == 0) *reinterpret_cast<float*>(xq + (g >> 2) * QW_SG_BYTES + 256 + (g & 3) * 4) = 0.0f;
+// exact Q8_0 codes of 8 values (reference q8.c:27-28), packed; out of line: it runs for ~1 value in 500
+__device__ __noinline__ uint2 q8_pack8_exact(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, float scale) {
+    const uint32_t w0 = (uint32_t) (q8_code(v0, scale) & 0xff) | (uint32_t) (q8_code(v1, scale) & 0xff) << 8
+                        | (uint32_t) (q8_code(v2, scale) & 0xff) << 16 | (uint32_t) (q8_code(v3, scale) & 0xff) << 24;
+    const uint32_t w1 = (uint32_t) (q8_code(v4, scale) & 0xff) | (uint32_t) (q8_code(v5, scale) & 0xff) << 8
+                        | (uint32_t) (q8_code(v6, scale) & 0xff) << 16 | (uint32_t) (q8_code(v7, scale) & 0xff) << 24;
+    return make_uint2(w0, w1);
 }
 
-constexpr int kMaxGroupsPerWarpNorm = 5; // D <= 5120 (Qwen3-32B); checked at init
+// One warp quantises one 256-column record: lane owns 8 consecutive values v[0..7] (group = lane / 8
+// of the record). Group absmax by 3 shuffles; scale = absmax / 127 with the reference's IEEE division.
+// Codes: the reference computes roundf(x / scale) (IEEE division, half away from zero, clamp). Here
+// t = x * rcp(scale) is within 2^-21 relative of the true quotient (|t| <= 127.01), so rintf(t) is the
+// reference's code unless t lies within 1e-3 of a rounding boundary k + 0.5 -- then (and for NaN or a
+// scale too small to invert) all 8 values take the exact path. Packed codes go out with one 8-byte STS
+// per lane. live = the lane's group exists (pad groups get zero codes, zero scale).
+__device__ __forceinline__ void quant_record(uint8_t* xq, int rec, int lane, const float (&v)[8], bool live) {
+    float amax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+    const float scale = q8_scale(amax);
+    const float rinv = __frcp_rn(scale);
+    bool bad = !(rinv <= 3.0e38f);
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float t = __fmul_rn(v[i], rinv);
+        const float r = rintf(t);
+        bad |= !(fabsf(__fsub_rn(t, r)) <= 0.499f);
+        const uint32_t c = (uint32_t) ((int) r & 0xff) << (8 * (i & 3));
+        if (i < 4) w0 |= c; else w1 |= c;
+    }
+    uint2 w = make_uint2(w0, w1);
+    if (bad) w = q8_pack8_exact(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], scale);
+    uint8_t* r = xq + (size_t) rec * QW_SG_BYTES;
+    *reinterpret_cast<uint2*>(r + lane * 8) = live ? w : make_uint2(0u, 0u);
+    if ((lane & 7) == 0) *reinterpret_cast<float*>(r + 256 + (lane >> 3) * 4) = live ? scale : 0.0f;
+}
 
-// x (fp32, D) -> RMSNorm with weights w -> Q8_0 codes + scales in shared memory (forward.c:254-259).
-// Warp w owns groups w, w+16, ...; all its loads are issued up front (one L2 round trip).
-// from_embedding: the residual stream starts as the dequantised embedding row (forward.c:237).
-__device__ void prologue_norm_quant(const Shared& sh, const MegaParams& p, const float* __restrict__ w, bool from_embedding) {
+constexpr int kRecBatch = 3; // records per warp and pass: 45 records = 11520 columns per pass
+
+// fp32 flow vector src[n] (written by other CTAs, polled) -> optional RMSNorm with weights nw
+// (forward.c:254-259; nw == nullptr: none) -> Q8_0 codes + scales in shared memory (q8.c:5-30).
+// Warp w owns records w, w + 15, w + 30 of a pass; all loads of a pass are issued up front (one L2
+// round trip). With RMSNorm the vector must fit one pass (checked at init).
+__device__ __forceinline__ void prologue_quant(const Shared& sh, const MegaParams& p, const float* src, int n, const float* __restrict__ nw) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D = p.D;
-    const int groups = D / 64, pad_groups = qw_pad_cols(D) / 64;
-    float va[kMaxGroupsPerWarpNorm], vb[kMaxGroupsPerWarpNorm];
-    if (from_embedding) {
-        const int tok = p.token_dev ? *p.token_dev : p.token;
-        const uint8_t* row = p.w_emb + (size_t) tok * qw_row_bytes(D);
+    const int groups = n / 64, recs = qw_sg_per_row(n);
+#pragma unroll 1
+    for (int pass0 = 0; pass0 < recs; pass0 += kRecBatch * kConsumerWarps) { // uniform over the CTA: it contains a barrier
+        const int r0 = pass0 + warp;
+        float v[kRecBatch][8];
+        uint4 a[kRecBatch], b[kRecBatch];
+        bool live[kRecBatch];
 #pragma unroll
-        for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
-            const int g = warp + k * kConsumerWarps;
-            va[k] = vb[k] = 0.0f;
-            if (g < groups) {
-                const uint8_t* rec = row + (size_t) (g >> 2) * QW_SG_BYTES;
-                const float sc = *reinterpret_cast<const float*>(rec + 256 + (g & 3) * 4);
-                const int8_t* codes = reinterpret_cast<const int8_t*>(rec + (g & 3) * 64);
-                va[k] = __fmul_rn((float) codes[lane], sc);
-                vb[k] = __fmul_rn((float) codes[lane + 32], sc);
-                if (blockIdx.x == 0) { // the residual stream lives in global memory; CTA 0 seeds it
-                    p.x[g * 64 + lane] = va[k];
-                    p.x[g * 64 + 32 + lane] = vb[k];
-                }
+        for (int k = 0; k < kRecBatch; ++k) {
+            const int rec = r0 + k * kConsumerWarps;
+            live[k] = rec < recs && rec * 4 + (lane >> 3) < groups;
+            if (live[k]) {
+                a[k] = ldf_u4(src + rec * 256 + lane * 8);
+                b[k] = ldf_u4(src + rec * 256 + lane * 8 + 4);
             }
         }
-    } else {
 #pragma unroll
-        for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
-            const int g = warp + k * kConsumerWarps;
-            va[k] = vb[k] = 0.0f;
-            if (g < groups) {
-                va[k] = __ldcg(p.x + g * 64 + lane);
-                vb[k] = __ldcg(p.x + g * 64 + 32 + lane);
+        for (int k = 0; k < kRecBatch; ++k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[k][i] = 0.0f;
+            if (live[k]) {
+                const float* q = src + (r0 + k * kConsumerWarps) * 256 + lane * 8;
+                if (unset4(a[k])) a[k] = poll4_slow(sh.abort_flag, p.err, q, 10);
+                if (unset4(b[k])) b[k] = poll4_slow(sh.abort_flag, p.err, q + 4, 10);
+                v[k][0] = __uint_as_float(a[k].x); v[k][1] = __uint_as_float(a[k].y);
+                v[k][2] = __uint_as_float(a[k].z); v[k][3] = __uint_as_float(a[k].w);
+                v[k][4] = __uint_as_float(b[k].x); v[k][5] = __uint_as_float(b[k].y);
+                v[k][6] = __uint_as_float(b[k].z); v[k][7] = __uint_as_float(b[k].w);
             }
         }
-    }
-    // norm weights: issued now so their latency overlaps the reduction (no L1 in this kernel: 1-2 us under load)
-    float wa[kMaxGroupsPerWarpNorm], wb[kMaxGroupsPerWarpNorm];
+        if (nw) {
+            float ss = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
-        const int g = warp + k * kConsumerWarps;
-        wa[k] = wb[k] = 0.0f;
-        if (g < groups) {
-            wa[k] = __ldg(w + g * 64 + lane);
-            wb[k] = __ldg(w + g * 64 + 32 + lane);
+            for (int k = 0; k < kRecBatch; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ss = __fmaf_rn(v[k][i], v[k][i], ss);
+            ss = warp_sum(ss);
+            if (lane == 0) sh.misc[warp] = ss;
+            bar_consumers();
+            float tot = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kConsumerWarps; ++i) tot = __fadd_rn(tot, sh.misc[i]);
+            const float r = rms_rscale(tot, n);
+#pragma unroll
+            for (int k = 0; k < kRecBatch; ++k) {
+                if (!live[k]) continue;
+                const float* g = nw + (r0 + k * kConsumerWarps) * 256 + lane * 8;
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(g)), g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+                v[k][0] = __fmul_rn(g0.x, __fmul_rn(r, v[k][0])); v[k][1] = __fmul_rn(g0.y, __fmul_rn(r, v[k][1]));
+                v[k][2] = __fmul_rn(g0.z, __fmul_rn(r, v[k][2])); v[k][3] = __fmul_rn(g0.w, __fmul_rn(r, v[k][3]));
+                v[k][4] = __fmul_rn(g1.x, __fmul_rn(r, v[k][4])); v[k][5] = __fmul_rn(g1.y, __fmul_rn(r, v[k][5]));
+                v[k][6] = __fmul_rn(g1.z, __fmul_rn(r, v[k][6])); v[k][7] = __fmul_rn(g1.w, __fmul_rn(r, v[k][7]));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kRecBatch; ++k) {
+            const int rec = r0 + k * kConsumerWarps;
+            if (rec < recs) quant_record(sh.xq, rec, lane, v[k], live[k]);
         }
     }
-    float ss = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) ss = __fadd_rn(ss, __fadd_rn(__fmul_rn(va[k], va[k]), __fmul_rn(vb[k], vb[k])));
-    ss = warp_sum(ss);
-    if (lane == 0) sh.misc[warp] = ss;
-    bar_consumers();
-    float tot = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kConsumerWarps; ++i) tot = __fadd_rn(tot, sh.misc[i]);
-    const float r = rms_rscale(tot, D);
-#pragma unroll
-    for (int k = 0; k < kMaxGroupsPerWarpNorm; ++k) {
-        const int g = warp + k * kConsumerWarps;
-        if (g < groups) {
-            const float a = __fmul_rn(wa[k], __fmul_rn(r, va[k]));
-            const float b = __fmul_rn(wb[k], __fmul_rn(r, vb[k]));
-            put_group(sh.xq, g, lane, a, b);
-        } else if (g < pad_groups) {
-            zero_group(sh.xq, g, lane);
-        }
-    }
-    bar_consumers();
+    bar_consumers(); // xq complete; also protects sh.misc against the next prologue
 }
 
-// fp32 vector in global memory (written by other CTAs) -> Q8_0 codes + scales in shared memory
-__device__ void prologue_quant_global(const Shared& sh, const float* src, int n) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int groups = n / 64, pad_groups = qw_pad_cols(n) / 64;
-    constexpr int kBatch = 10; // Hd 9728 -> 152 groups -> 9.5 per warp: one round trip
-    for (int g0 = warp; g0 < pad_groups; g0 += kBatch * kConsumerWarps) {
-        float va[kBatch], vb[kBatch];
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            const int g = g0 + k * kConsumerWarps;
-            va[k] = vb[k] = 0.0f;
-            if (g < groups) {
-                va[k] = __ldcg(src + g * 64 + lane);
-                vb[k] = __ldcg(src + g * 64 + 32 + lane);
-            }
+// already-quantised flow vector (attention output, SG layout: codes and scales, polled) -> shared.
+// Words of pad groups (columns >= n) are never written by anyone: they are zero here.
+__device__ void prologue_load_codes(const Shared& sh, const MegaParams& p, const uint8_t* q, int n) {
+    const int pieces = (int) (qw_row_bytes(n) / 16), groups = n / 64;
+    for (int i = threadIdx.x; i < pieces; i += kConsumerThreads) {
+        const int rec = i / 17, k = i % 17; // 17 x 16 B per record: 16 code pieces, then the 4 scales
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (k < 16) {
+            if (rec * 4 + (k >> 2) < groups) v = poll4(sh, p, q + (size_t) i * 16, 12);
+        } else if (rec * 4 + 3 < groups) {
+            v = poll4(sh, p, q + (size_t) i * 16, 12);
+        } else { // a record with pad groups: poll only the live scales
+            uint32_t s[4] = {0u, 0u, 0u, 0u};
+            for (int g = 0; g < 4; ++g)
+                if (rec * 4 + g < groups) s[g] = __float_as_uint(poll1(sh, p, reinterpret_cast<const float*>(q + (size_t) i * 16) + g, 12));
+            v = make_uint4(s[0], s[1], s[2], s[3]);
         }
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            const int g = g0 + k * kConsumerWarps;
-            if (g < groups) put_group(sh.xq, g, lane, va[k], vb[k]);
-            else if (g < pad_groups) zero_group(sh.xq, g, lane);
-        }
+        reinterpret_cast<uint4*>(sh.xq)[i] = v;
     }
-    bar_consumers();
-}
-
-// already-quantised vector (attention output, SG layout in global) -> shared
-__device__ void prologue_load_codes(const Shared& sh, const uint8_t* q, int n) {
-    const int bytes = (int) qw_row_bytes(n);
-    for (int i = threadIdx.x; i < bytes / 16; i += kConsumerThreads)
-        reinterpret_cast<int4*>(sh.xq)[i] = __ldcg(reinterpret_cast<const int4*>(q) + i);
     bar_consumers();
 }
 
 // ---------------------------------------------------------------- consumer: attention
-// scratch (floats, inside sh.scr): raw[1280] | sq[1280] | scores[4 groups][8 heads][32]
-constexpr int kScrRaw = 0, kScrQ = 1280, kScrS = 2560;
-constexpr int kScrFloats = kScrS + 4 * 8 * 32;
+// RMSNorm weight + RoPE for a 128-wide head (forward.c:267-280, 104-118); cos/sin come from the
+// host-computed table so the angles are the reference's bit for bit. One warp per head: lane owns
+// the pairs (lane, lane + 64) and (lane + 32, lane + 96).
+__device__ __forceinline__ void head_norm_rope_warp(float* dst, const float x[4], const float* g, const MegaParams& p, int lane) {
+    // x[0..3] = raw[lane], raw[lane + 32], raw[lane + 64], raw[lane + 96]
+    float ss = __fmul_rn(x[0], x[0]);
+    ss = __fmaf_rn(x[1], x[1], ss);
+    ss = __fmaf_rn(x[2], x[2], ss);
+    ss = __fmaf_rn(x[3], x[3], ss);
+    const float r = rms_rscale(warp_sum(ss), 128);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = lane + 32 * k; // 0..63
+        const float c = __ldg(p.rope_cos + (size_t) p.pos * 64 + j), s = __ldg(p.rope_sin + (size_t) p.pos * 64 + j);
+        const float a = __fmul_rn(__ldg(g + j), __fmul_rn(r, x[k]));
+        const float b = __fmul_rn(__ldg(g + j + 64), __fmul_rn(r, x[2 + k]));
+        dst[j] = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, s));
+        dst[j + 64] = __fadd_rn(__fmul_rn(a, s), __fmul_rn(b, c));
+    }
+}
 
-// RMSNorm weight + RoPE for element i of a 128-wide head (forward.c:267-280, 104-118);
-// cos/sin come from the host-computed table so the angles are the reference's bit for bit.
-struct RopeCoef { // this thread's constants for element i of any head: loaded once per attention phase
-    float c, s, glo, ghi;
+// Online-softmax state of one warp for HW query heads: lane owns output dims 4*lane .. 4*lane+3 of
+// every head; m and l are kept per head in every lane (identical across the warp).
+template <int HW>
+struct AttnState {
+    float4 acc[HW];
+    float m[HW], l[HW];
 };
-__device__ __forceinline__ RopeCoef rope_coef(const float* g, const MegaParams& p, int i) {
-    const int j = i & 63;
-    return {__ldg(p.rope_cos + (size_t) p.pos * 64 + j), __ldg(p.rope_sin + (size_t) p.pos * 64 + j), __ldg(g + j), __ldg(g + j + 64)};
-}
-__device__ __forceinline__ float head_norm_rope(const float* raw, const RopeCoef& k, float r, int i) {
-    const int j = i & 63;
-    const float a = __fmul_rn(k.glo, __fmul_rn(r, raw[j]));
-    const float b = __fmul_rn(k.ghi, __fmul_rn(r, raw[j + 64]));
-    return (i < 64) ? __fsub_rn(__fmul_rn(a, k.c), __fmul_rn(b, k.s)) : __fadd_rn(__fmul_rn(a, k.s), __fmul_rn(b, k.c));
-}
-// sum of squares over 128 values by one warp (4 per lane, then the shuffle tree)
-__device__ __forceinline__ float head_rscale_warp(const float* raw, int lane) {
-    const float4 v = *reinterpret_cast<const float4*>(raw + lane * 4);
-    float ss = __fmul_rn(v.x, v.x);
-    ss = __fmaf_rn(v.y, v.y, ss);
-    ss = __fmaf_rn(v.z, v.z, ss);
-    ss = __fmaf_rn(v.w, v.w, ss);
-    return rms_rscale(warp_sum(ss), 128);
+template <int HW>
+__device__ __forceinline__ void attn_state_reset(AttnState<HW>& st) {
+#pragma unroll
+    for (int j = 0; j < HW; ++j) {
+        st.acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        st.m[j] = -INFINITY;
+        st.l[j] = 0.0f;
+    }
 }
 
-// Split-KV attention for the units of this CTA. The 16 consumer warps form 4 groups of 4 warps;
-// each group takes whole 28-position tiles (unit i of a segment -> group i % 4) and runs the three
-// stages of a tile -- scores, online-softmax update, P.V -- synchronised by its OWN named barrier
-// (128 threads), so four tiles are in flight per SM and no CTA-wide barrier sits in the tile loop.
-//   scores : 8 lanes per position (lane covers float4 columns sub, sub+8, sub+16, sub+24 -> every
-//            quarter-warp reads 128 contiguous bytes of K), all KV_MUL heads, 3-step shuffle tree;
-//   softmax: warp w of the group owns heads w, w+4; lane = position;
-//   P.V    : thread = (head, 4 output dims), float4 accumulator in registers.
-// A segment = the CTA's units of one KV head; its query heads (and, if the CTA owns the last
-// chunk, this step's own K/V row: RMSNorm + RoPE, written to the cache for later steps) are
-// prepared once per segment with CTA-wide barriers, and the 4 group states are merged at its end.
-constexpr int kAttnGroups = 4, kAttnGT = 128;
-__device__ __forceinline__ void bar_group(int grp) {
-    asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(kAttnGT) : "memory");
+// One warp attends over `cnt` positions (K rows at Kt, V rows at Vt, 128 floats each, shared memory)
+// for HW query heads q[j] (this lane's 4 dims of each head). Scores (forward.c:156-165): every lane
+// forms its 4-dim partial dot for PB = 32 / HW positions x HW heads = 32 values, and a butterfly
+// transpose-reduction (31 shuffles) leaves lane i with the full dot of value i = (position i / HW,
+// head i % HW). Softmax statistics per head by shuffles over the lanes of that head, then P.V with
+// the probability broadcast from its lane. No shared-memory traffic besides one LDS.128 per K row
+// and per V row, and no synchronisation with other warps.
+template <int HW>
+__device__ __forceinline__ void attn_rows(const float* Kt, const float* Vt, int cnt, const float4 (&q)[HW], AttnState<HW>& st, int lane) {
+    constexpr int PB = 32 / HW;
+    const float inv = sqrtf(128.0f);
+#pragma unroll 1
+    for (int b0 = 0; b0 < cnt; b0 += PB) {
+        const int nb = min(PB, cnt - b0);
+        float v[32];
+#pragma unroll
+        for (int pp = 0; pp < PB; ++pp) {
+            const int r = b0 + min(pp, nb - 1); // rows past the end recompute a valid row (masked below)
+            const float4 kf = *reinterpret_cast<const float4*>(Kt + r * 128 + lane * 4);
+#pragma unroll
+            for (int j = 0; j < HW; ++j) {
+                float d = __fmul_rn(q[j].x, kf.x);
+                d = __fmaf_rn(q[j].y, kf.y, d);
+                d = __fmaf_rn(q[j].z, kf.z, d);
+                d = __fmaf_rn(q[j].w, kf.w, d);
+                v[pp * HW + j] = d;
+            }
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const bool hi = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                const float send = hi ? v[i] : v[i + s];
+                const float keep = hi ? v[i + s] : v[i];
+                v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, s));
+            }
+        }
+        const int pp = lane / HW;
+        const float sc = pp < nb ? __fdiv_rn(v[0], inv) : -INFINITY; // score / sqrtf(head_dim)
+        float bm = sc;
+#pragma unroll
+        for (int o = HW; o < 32; o <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        // every lane learns the block max of every head (lane j holds head j's)
+        float e = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HW; ++j) {
+            const float bmj = __shfl_sync(0xffffffffu, bm, j);
+            const float m_new = fmaxf(st.m[j], bmj);
+            const float scl = (st.m[j] == -INFINITY) ? 0.0f : expf(__fsub_rn(st.m[j], m_new));
+            if ((lane % HW) == j) e = pp < nb ? expf(__fsub_rn(sc, m_new)) : 0.0f;
+            st.m[j] = m_new;
+            st.l[j] = __fmul_rn(st.l[j], scl);
+            st.acc[j].x = __fmul_rn(st.acc[j].x, scl);
+            st.acc[j].y = __fmul_rn(st.acc[j].y, scl);
+            st.acc[j].z = __fmul_rn(st.acc[j].z, scl);
+            st.acc[j].w = __fmul_rn(st.acc[j].w, scl);
+        }
+        float es = e;
+#pragma unroll
+        for (int o = HW; o < 32; o <<= 1) es = __fadd_rn(es, __shfl_xor_sync(0xffffffffu, es, o));
+#pragma unroll
+        for (int j = 0; j < HW; ++j) st.l[j] = __fadd_rn(st.l[j], __shfl_sync(0xffffffffu, es, j));
+#pragma unroll 2
+        for (int i = 0; i < nb; ++i) { // uniform across the warp
+            const float4 vv = *reinterpret_cast<const float4*>(Vt + (b0 + i) * 128 + lane * 4);
+#pragma unroll
+            for (int j = 0; j < HW; ++j) {
+                const float pw = __shfl_sync(0xffffffffu, e, i * HW + j);
+                st.acc[j].x = __fmaf_rn(pw, vv.x, st.acc[j].x);
+                st.acc[j].y = __fmaf_rn(pw, vv.y, st.acc[j].y);
+                st.acc[j].z = __fmaf_rn(pw, vv.z, st.acc[j].z);
+                st.acc[j].w = __fmaf_rn(pw, vv.w, st.acc[j].w);
+            }
+        }
+    }
 }
 
+// merge another warp's dumped state (shared memory, [HW][kPartStride]) into this warp's
+template <int HW>
+__device__ __forceinline__ void attn_merge_in(AttnState<HW>& st, const float* slot, int lane) {
+#pragma unroll
+    for (int j = 0; j < HW; ++j) {
+        const float m2 = slot[j * kPartStride + 128], l2 = slot[j * kPartStride + 129];
+        const float4 a2 = *reinterpret_cast<const float4*>(slot + j * kPartStride + lane * 4);
+        const float M = fmaxf(st.m[j], m2);
+        const float wa = (st.m[j] == -INFINITY) ? 0.0f : expf(__fsub_rn(st.m[j], M));
+        const float wb = (m2 == -INFINITY) ? 0.0f : expf(__fsub_rn(m2, M));
+        st.acc[j].x = __fmaf_rn(a2.x, wb, __fmul_rn(st.acc[j].x, wa));
+        st.acc[j].y = __fmaf_rn(a2.y, wb, __fmul_rn(st.acc[j].y, wa));
+        st.acc[j].z = __fmaf_rn(a2.z, wb, __fmul_rn(st.acc[j].z, wa));
+        st.acc[j].w = __fmaf_rn(a2.w, wb, __fmul_rn(st.acc[j].w, wa));
+        st.l[j] = __fmaf_rn(l2, wb, __fmul_rn(st.l[j], wa));
+        st.m[j] = M;
+    }
+}
+template <int HW>
+__device__ __forceinline__ void attn_dump(const AttnState<HW>& st, float* slot, int lane) {
+#pragma unroll
+    for (int j = 0; j < HW; ++j) {
+        *reinterpret_cast<float4*>(slot + j * kPartStride + lane * 4) = st.acc[j];
+        if (lane == 0) {
+            slot[j * kPartStride + 128] = st.m[j];
+            slot[j * kPartStride + 129] = st.l[j];
+        }
+    }
+}
+
+// shared scratch (floats, inside sh.scr): the segment's heads sq[KV_MUL*128 q | 128 k | 128 v]; after the
+// tiles the same memory holds up to 8 dumped warp states for the merge tree.
+constexpr int kScrFloats = 8 * 4 * kPartStride;
+
+// Split-KV attention for the tiles of this CTA. A segment = the CTA's tiles of one KV head; its query
+// heads (and, if the CTA owns the KV head's last chunk, this step's own K/V row: RMSNorm + RoPE,
+// written to the cache for later steps) are prepared once per segment, one warp per head. Warp w
+// serves head group w % NHG; the warps of a head group split the segment's cached positions into
+// equal contiguous ranges (a range may straddle two tiles), so the load is balanced at any context
+// length. Every warp walks every tile for the ring protocol.
 template <int KV_MUL>
 __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsigned& it) {
-    constexpr int NACC = (KV_MUL * 32 + kAttnGT - 1) / kAttnGT; // float4 accumulators per thread
+    constexpr int HW = KV_MUL < 4 ? KV_MUL : 4; // heads per warp
+    constexpr int NHG = KV_MUL / HW;            // head groups per KV head
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = warp >> 2, gw = warp & 3, gt = tid & (kAttnGT - 1);
-    float* raw = sh.scr + kScrRaw;   // [KV_MUL*128 q | 128 k | 128 v] raw projections; reused as flush scratch
-    float* sq = sh.scr + kScrQ;      // [KV_MUL*128] normalised + rotated q, then [128] k, [128] v of this step
-    float* sc = sh.scr + kScrS + grp * (8 * 32); // this group's scores / probabilities [head][32]
-    float* s_r = sh.misc + 16;
-    float* g_m = sh.misc + 64 + grp * 32;  // running max per head
-    float* g_l = g_m + 8;                  // running sum per head
-    float* g_scale = g_m + 16;             // rescale factor of the last update
+    float* sq = sh.scr;
     int nc, u0, u1;
     attn_units(p, nc, u0, u1);
+    float* fl = flow_layer(p, l);
+    const float* qkv = fl + p.o_qkv;
     const float* gq = p.q_norm + (size_t) l * 128;
     const float* gk = p.k_norm + (size_t) l * 128;
-    const float inv = sqrtf(128.0f);
     const unsigned it_base = it;
-    float4 acc[NACC];
-    // element e = tid & 127 is the one this thread normalises/rotates for every head (the strides are
-    // multiples of 128): fetch its cos/sin and norm weights now, off the critical path (no L1 here)
-    const RopeCoef kq = rope_coef(gq, p, tid & 127), kk = rope_coef(gk, p, tid & 127);
-
-    // one tile: cnt positions, K rows at Kt, V rows at Vt (shared memory)
-    auto tile = [&](const float* Kt, const float* Vt, int cnt) {
-        // ---- scores (forward.c:156-165)
-        const int sub = gt & 7;
-#pragma unroll 1
-        for (int r = 0; r < 2; ++r) {
-            const int pos = r * 16 + (gt >> 3);
-            const int pc = min(pos, cnt - 1); // idle lanes recompute a valid row: uniform control flow for the shuffles
-            float d[KV_MUL];
-#pragma unroll
-            for (int j = 0; j < KV_MUL; ++j) d[j] = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 kf = *reinterpret_cast<const float4*>(Kt + pc * 128 + (sub + 8 * i) * 4);
-#pragma unroll
-                for (int j = 0; j < KV_MUL; ++j) {
-                    const float4 qf = *reinterpret_cast<const float4*>(sq + j * 128 + (sub + 8 * i) * 4);
-                    d[j] = __fmaf_rn(qf.x, kf.x, d[j]);
-                    d[j] = __fmaf_rn(qf.y, kf.y, d[j]);
-                    d[j] = __fmaf_rn(qf.z, kf.z, d[j]);
-                    d[j] = __fmaf_rn(qf.w, kf.w, d[j]);
-                }
-            }
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-#pragma unroll
-                for (int j = 0; j < KV_MUL; ++j) d[j] = __fadd_rn(d[j], __shfl_xor_sync(0xffffffffu, d[j], o));
-            }
-            if (sub == 0 && pos < cnt) {
-#pragma unroll
-                for (int j = 0; j < KV_MUL; ++j) sc[j * 32 + pos] = __fdiv_rn(d[j], inv); // score / sqrtf(head_dim)
-            }
-        }
-        bar_group(grp);
-        // ---- online softmax update: warp gw owns heads gw, gw+4; lane = position
-        for (int j = gw; j < KV_MUL; j += 4) {
-            const float s = lane < cnt ? sc[j * 32 + lane] : -INFINITY;
-            const float m_old = g_m[j];
-            const float m_new = fmaxf(m_old, warp_max(s));
-            const float e = lane < cnt ? expf(__fsub_rn(s, m_new)) : 0.0f;
-            if (lane < cnt) sc[j * 32 + lane] = e;
-            const float lsum = warp_sum(e);
-            if (lane == 0) {
-                const float scl = (m_old == -INFINITY) ? 0.0f : expf(__fsub_rn(m_old, m_new));
-                g_scale[j] = scl;
-                g_l[j] = __fmaf_rn(g_l[j], scl, lsum);
-                g_m[j] = m_new;
-            }
-        }
-        bar_group(grp);
-        // ---- P.V: thread = (head j, dims 4*d4 .. 4*d4+3)
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-            const int idx = gt + k * kAttnGT;
-            if (idx < KV_MUL * 32) {
-                const int j = idx >> 5, d4 = idx & 31;
-                const float scl = g_scale[j];
-                float4 a = acc[k];
-                a.x = __fmul_rn(a.x, scl); a.y = __fmul_rn(a.y, scl); a.z = __fmul_rn(a.z, scl); a.w = __fmul_rn(a.w, scl);
-                for (int i = 0; i < cnt; ++i) {
-                    const float pw = sc[j * 32 + i];
-                    const float4 vv = *reinterpret_cast<const float4*>(Vt + i * 128 + d4 * 4);
-                    a.x = __fmaf_rn(pw, vv.x, a.x); a.y = __fmaf_rn(pw, vv.y, a.y);
-                    a.z = __fmaf_rn(pw, vv.z, a.z); a.w = __fmaf_rn(pw, vv.w, a.w);
-                }
-                acc[k] = a;
-            }
-        }
-        bar_group(grp); // sc / g_scale are rewritten by this group's next tile
-    };
+    const unsigned U = (unsigned) (p.KVHl * nc);
+    const int hg = warp % NHG;                                   // this warp's head group
+    const int wi = warp / NHG;                                   // its index among the warps of the group
+    const int wn = (kConsumerWarps - hg + NHG - 1) / NHG;        // warps in the group
 
     int u = u0;
     while (u < u1) {
         const int kvh = u / nc;
         const int seg_end = min(u1, (kvh + 1) * nc);
         const bool own_last = seg_end == (kvh + 1) * nc; // the segment contains the KV head's last chunk
-        // ---- segment prologue (CTA-wide): q heads, and this step's K/V row if we own the last chunk
-        const int nraw = KV_MUL * 128 + (own_last ? 256 : 0);
-        bar_consumers();
-        for (int i = tid; i < nraw; i += kConsumerThreads) {
-            const float* src = i < KV_MUL * 128 ? p.qkv + (size_t) kvh * KV_MUL * 128 + i
-                               : i < KV_MUL * 128 + 128 ? p.qkv + p.Pl + (size_t) kvh * 128 + (i - KV_MUL * 128)
-                                                        : p.qkv + p.Pl + p.Kl + (size_t) kvh * 128 + (i - KV_MUL * 128 - 128);
-            raw[i] = __ldcg(src);
-        }
-        bar_consumers();
-        if (warp < KV_MUL + (own_last ? 1 : 0)) {
-            const float r = head_rscale_warp(raw + warp * 128, lane);
-            if (lane == 0) s_r[warp] = r;
-        }
-        bar_consumers();
-        for (int i = tid; i < nraw; i += kConsumerThreads) {
-            const int hd = i >> 7, e = i & 127;
-            if (hd < KV_MUL) {
-                sq[i] = head_norm_rope(raw + hd * 128, kq, s_r[hd], e);
+        // ---- segment prologue: warp j < KV_MUL prepares query head j; warps KV_MUL, KV_MUL+1 this step's K, V row
+        bar_consumers(); // previous users of the scratch are done
+        if (warp < KV_MUL + (own_last ? 2 : 0)) {
+            const float* src = warp < KV_MUL ? qkv + (size_t) (kvh * KV_MUL + warp) * 128
+                               : warp == KV_MUL ? qkv + p.Pl + (size_t) kvh * 128
+                                                : qkv + p.Pl + p.Kl + (size_t) kvh * 128;
+            float x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = __uint_as_float(ldf_u32(src + lane + 32 * k));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (__float_as_uint(x[k]) == kSent) x[k] = poll1(sh, p, src + lane + 32 * k, 13);
+            float* dst = sq + warp * 128;
+            if (warp <= KV_MUL) {
+                head_norm_rope_warp(dst, x, warp < KV_MUL ? gq : gk, p, lane);
             } else {
-                const size_t coff = (((size_t) l * p.KVHl + kvh) * p.S + p.pos) * 128;
-                if (hd == KV_MUL) {
-                    const float kx = head_norm_rope(raw + hd * 128, kk, s_r[hd], e);
-                    sq[i] = kx;
-                    p.k_cache[coff + e] = kx;
-                } else {
-                    sq[i] = raw[i];
-                    p.v_cache[coff + e] = raw[i];
-                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = x[k];
+            }
+            if (warp >= KV_MUL) { // this step's K / V row goes into the cache for later steps
+                __syncwarp();
+                float* cache = (warp == KV_MUL ? p.k_cache : p.v_cache) + (((size_t) l * p.KVHl + kvh) * p.S + p.pos) * 128;
+                *reinterpret_cast<float4*>(cache + lane * 4) = *reinterpret_cast<const float4*>(dst + lane * 4);
             }
         }
-        if (gt < 8) {
-            g_m[gt] = -INFINITY;
-            g_l[gt] = 0.0f;
-            g_scale[gt] = 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         bar_consumers();
-        // ---- tiles of the segment: every warp walks every tile (ring protocol), its group works on every 4th
-        for (int uu = u; uu < seg_end; ++uu) {
-            const unsigned itx = it_base + (unsigned) (uu - u0);
-            const unsigned slot = itx % p.nslot, par = (itx / p.nslot) & 1;
-            mbar_wait(sh, p, sh.full + slot * 8, par, 4);
-            if (((uu - u) & (kAttnGroups - 1)) == grp) {
-                const int p0 = (uu - kvh * nc) * kChunk;
-                const int cnt = min(p.pos, p0 + kChunk) - p0; // cached positions in the tile
-                const float* Kt = reinterpret_cast<const float*>(sh.ring + (size_t) slot * kSlotBytes);
-                if (cnt > 0) tile(Kt, Kt + kChunk * 128, cnt);
+        // ---- this warp's share of the segment's cached positions
+        const int ntile = seg_end - u;
+        const int pbase = (u - kvh * nc) * kChunk;                           // first position of the segment
+        const int npos = max(0, min(p.pos, pbase + ntile * kChunk) - pbase); // cached positions in the segment
+        const int my0 = (int) ((long long) npos * wi / wn), my1 = (int) ((long long) npos * (wi + 1) / wn);
+        float4 q[HW];
+#pragma unroll
+        for (int j = 0; j < HW; ++j) q[j] = *reinterpret_cast<const float4*>(sq + (hg * HW + j) * 128 + lane * 4);
+        AttnState<HW> st;
+        attn_state_reset(st);
+        // tiles of the segment, then (t == ntile) this step's own position from shared memory, which the
+        // last warp of each head group takes -- one call site of attn_rows keeps the code small
+#pragma unroll 1
+        for (int t = 0; t <= ntile; ++t) {
+            const float *Kt, *Vt;
+            int cnt = 0;
+            unsigned slot = 0;
+            if (t < ntile) {
+                const unsigned itx = it_base + (unsigned) (u - u0 + t);
+                slot = itx % p.nslot;
+                mbar_wait(sh, p, sh.full + slot * 8, (itx / p.nslot) & 1, 4);
+                const int a = max(my0, t * kChunk) - t * kChunk, b = min(my1, (t + 1) * kChunk) - t * kChunk;
+                Kt = reinterpret_cast<const float*>(sh.ring + (size_t) slot * kSlotBytes) + a * 128;
+                Vt = Kt + kChunk * 128;
+                cnt = b - a;
+            } else {
+                Kt = sq + KV_MUL * 128;
+                Vt = Kt + 128;
+                cnt = (own_last && wi == wn - 1) ? 1 : 0;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+            if (cnt > 0) attn_rows<HW>(Kt, Vt, cnt, q, st, lane);
+            if (t < ntile) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+            }
         }
-        if (own_last && grp == 0) tile(sq + KV_MUL * 128, sq + KV_MUL * 128 + 128, 1); // this step's own position
-        // ---- merge the 4 group states (online-softmax merge) and publish (m, l, acc) for the combine phase
-        bar_consumers();
-        float* red = raw; // [grp][head][132]; raw/sq are dead now
-        constexpr int HP = KV_MUL < 4 ? KV_MUL : 4; // heads per pass (scratch is 2560 floats)
-#pragma unroll
-        for (int h0 = 0; h0 < KV_MUL; h0 += HP) {
-#pragma unroll
-            for (int k = 0; k < NACC; ++k) {
-                const int idx = gt + k * kAttnGT;
-                const int j = idx >> 5, d4 = idx & 31;
-                if (idx < KV_MUL * 32 && j >= h0 && j < h0 + HP)
-                    *reinterpret_cast<float4*>(red + (grp * HP + (j - h0)) * 132 + d4 * 4) = acc[k];
-            }
-            if (gt < HP) {
-                red[(grp * HP + gt) * 132 + 128] = g_m[h0 + gt];
-                red[(grp * HP + gt) * 132 + 129] = g_l[h0 + gt];
-            }
+        // ---- merge the warp states pairwise through shared memory (w <- w + half keeps w % NHG)
+        bar_consumers(); // sq is dead from here
+#pragma unroll 1
+        for (int half = 8; half >= NHG; half >>= 1) {
+            if (warp >= half && warp < 2 * half) attn_dump<HW>(st, sh.scr + (warp - half) * (HW * kPartStride), lane);
             bar_consumers();
-            if (tid < HP * 128) {
-                const int j = tid >> 7, d = tid & 127;
-                float M = -INFINITY;
+            if (warp < half && warp + half < kConsumerWarps) attn_merge_in<HW>(st, sh.scr + warp * (HW * kPartStride), lane);
+            bar_consumers();
+        }
+        // ---- publish (m, l, acc) of this CTA for the segment's heads
+        if (warp < NHG) {
+            const int blo = block_of_unit((unsigned) (kvh * nc), U, gridDim.x);
+            const int slot = my_block(p.perm) - blo;
+            float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + slot) * KV_MUL + warp * HW) * kPartStride;
 #pragma unroll
-                for (int g = 0; g < kAttnGroups; ++g) M = fmaxf(M, red[(g * HP + j) * 132 + 128]);
-                float L = 0.0f, A = 0.0f;
-#pragma unroll
-                for (int g = 0; g < kAttnGroups; ++g) {
-                    const float mg = red[(g * HP + j) * 132 + 128];
-                    const float e = (mg == -INFINITY) ? 0.0f : expf(__fsub_rn(mg, M));
-                    L = __fmaf_rn(red[(g * HP + j) * 132 + 129], e, L);
-                    A = __fmaf_rn(red[(g * HP + j) * 132 + d], e, A);
-                }
-                const int h = kvh * KV_MUL + h0 + j;
-                const size_t slot = (size_t) h * gridDim.x + attn_block(p);
-                p.part_acc[slot * 128 + d] = A;
-                if (d == 0) {
-                    p.part_m[slot] = M;
-                    p.part_l[slot] = L;
+            for (int j = 0; j < HW; ++j) {
+                stf_f4(dst + j * kPartStride + lane * 4, st.acc[j]);
+                if (lane == 0) {
+                    stf_f32(dst + j * kPartStride + 128, st.m[j]);
+                    stf_f32(dst + j * kPartStride + 129, st.l[j]);
                 }
             }
-            bar_consumers();
+            __threadfence(); // flush (see consume_mat)
         }
         u = seg_end;
     }
     it = it_base + (unsigned) (u1 - u0);
 }
 
-__device__ void consume_attn_dispatch(const Shared& sh, const MegaParams& p, int l, unsigned& it) {
-    switch (p.kv_mul) {
-        case 1: consume_attn<1>(sh, p, l, it); break;
-        case 2: consume_attn<2>(sh, p, l, it); break;
-        case 4: consume_attn<4>(sh, p, l, it); break;
-        default: consume_attn<8>(sh, p, l, it); break;
+// Combine task (head h, half hf): one warp merges the published partials of the head (online-softmax
+// merge over the CTAs that attended its KV head), divides by the sum (forward.c:60-75), writes the
+// fp32 result (debug read-back) and the Q8_0 group -- 64 codes + scale -- straight into the flow
+// vector the wo GEMV loads. Lane owns dims 64*hf + lane and 64*hf + 32 + lane. The partials are taken
+// 32 at a time (lane i polls m, l of slot i), chunks are folded with a running maximum.
+__device__ __noinline__ void combine_task(const Shared& sh, const MegaParams& p, int l, int h, int hf, int lane) {
+    float* fl = flow_layer(p, l);
+    const int nc = p.pos / kChunk + 1;
+    const unsigned U = (unsigned) (p.KVHl * nc), G = gridDim.x;
+    const int kvh = h / p.kv_mul, j = h % p.kv_mul;
+    const unsigned ulo = (unsigned) (kvh * nc), uhi = ulo + nc;
+    const int blo = block_of_unit(ulo, U, G), bhi = block_of_unit(uhi - 1, U, G);
+    const int nb = bhi - blo + 1;
+    const float* part = fl + p.o_part + ((size_t) kvh * p.part_slots * p.kv_mul + j) * kPartStride;
+    const size_t sstride = (size_t) p.kv_mul * kPartStride; // between slots
+    const int d0 = hf * 64 + lane;
+    float M = -INFINITY, Ls = 0.0f, A0 = 0.0f, A1 = 0.0f;
+#pragma unroll 1
+    for (int base = 0; base < nb; base += 32) {
+        const int n = min(32, nb - base);
+        float m = -INFINITY, lsum = 0.0f;
+        if (lane < n) {
+            const unsigned b = (unsigned) (blo + base + lane);
+            if (U * b / G < U * (b + 1) / G) { // the block has tiles (of this KV head, or it would not lie inside)
+                m = poll1(sh, p, part + (base + lane) * sstride + 128, 14);
+                lsum = poll1(sh, p, part + (base + lane) * sstride + 129, 14);
+            }
+        }
+        const float Mn = fmaxf(M, warp_max(m));
+        const float resc = (M == -INFINITY) ? 0.0f : expf(__fsub_rn(M, Mn));
+        const float w = (m == -INFINITY) ? 0.0f : expf(__fsub_rn(m, Mn)); // weight of this lane's slot
+        Ls = __fmaf_rn(Ls, resc, warp_sum(__fmul_rn(lsum, w)));
+        A0 = __fmul_rn(A0, resc);
+        A1 = __fmul_rn(A1, resc);
+        M = Mn;
+#pragma unroll 1
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            float a0[4], a1[4], wk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                wk[k] = __shfl_sync(0xffffffffu, w, (i0 + k) & 31);
+                a0[k] = a1[k] = 0.0f;
+                if (i0 + k < n && wk[k] != 0.0f) {
+                    a0[k] = __uint_as_float(ldf_u32(part + (base + i0 + k) * sstride + d0));
+                    a1[k] = __uint_as_float(ldf_u32(part + (base + i0 + k) * sstride + d0 + 32));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k < n && wk[k] != 0.0f) {
+                    if (__float_as_uint(a0[k]) == kSent) a0[k] = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + (base + i0 + k) * sstride + d0, 14));
+                    if (__float_as_uint(a1[k]) == kSent) a1[k] = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + (base + i0 + k) * sstride + d0 + 32, 14));
+                    A0 = __fmaf_rn(a0[k], wk[k], A0);
+                    A1 = __fmaf_rn(a1[k], wk[k], A1);
+                }
+            }
+        }
     }
+    const float o0 = __fdiv_rn(A0, Ls), o1 = __fdiv_rn(A1, Ls);
+    p.att[(size_t) h * 128 + d0] = o0;
+    p.att[(size_t) h * 128 + d0 + 32] = o1;
+    // quantise the group (q8.c:5-30) and store packed code words + scale
+    const float scale = q8_scale(warp_max(fmaxf(fabsf(o0), fabsf(o1))));
+    const uint32_t c0 = (uint32_t) (q8_code(o0, scale) & 0xff), c1 = (uint32_t) (q8_code(o1, scale) & 0xff);
+    uint32_t w0 = c0, w1 = c1;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        w0 |= __shfl_down_sync(0xffffffffu, c0, k) << (8 * k);
+        w1 |= __shfl_down_sync(0xffffffffu, c1, k) << (8 * k);
+    }
+    const int g = h * 2 + hf;
+    uint8_t* rec = reinterpret_cast<uint8_t*>(fl + p.o_attq) + (size_t) (g >> 2) * QW_SG_BYTES;
+    if ((lane & 3) == 0) {
+        stf_u32(rec + (g & 3) * 64 + lane, w0);
+        stf_u32(rec + (g & 3) * 64 + 32 + lane, w1);
+    }
+    if (lane == 0) stf_f32(reinterpret_cast<float*>(rec + 256 + (g & 3) * 4), scale);
+    __threadfence(); // flush (see consume_mat)
 }
 
-// merge the split-KV partials of each head (online-softmax merge), write fp32 att (debug
-// read-back) and its Q8_0 codes straight into the SG-layout vector the wo GEMV loads.
-__device__ void combine_attn(const Shared& sh, const MegaParams& p) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* mm = sh.scr;          // [kMaxGrid]
-    float* ww = sh.scr + 256;    // [kMaxGrid]
-    float* ll = sh.scr + 512;    // [kMaxGrid]
-    float* red = sh.scr + 768;   // [4][128]
-    float* so = sh.scr + 1280;   // [128]
-    const int nc = p.pos / kChunk + 1;
-    const long long U = (long long) p.KVHl * nc;
-    const int G = gridDim.x;
-    for (int h = blockIdx.x; h < p.Hl; h += G) {
-        const int kvh = h / p.kv_mul;
-        const long long ulo = (long long) kvh * nc, uhi = ulo + nc;
-        const int blo = max((int) (ulo * G / U) - 1, 0), bhi = min((int) (uhi * G / U) + 1, G - 1);
-        const int nb = bhi - blo + 1;
-        // all global loads of this head are issued up front (one L2 round trip): m, l by the first nb
-        // threads, the nb partial accumulators by (dim, part) threads, 4 parts x up to 8 each
-        const int d = tid & 127, part = tid >> 7;
-        constexpr int kMaxPer = 8;
-        float av[kMaxPer];
-#pragma unroll
-        for (int k = 0; k < kMaxPer; ++k) {
-            const int i = part + 4 * k;
-            av[k] = i < nb ? __ldcg(p.part_acc + ((size_t) h * G + blo + i) * 128 + d) : 0.0f;
-        }
-        float my_m = -INFINITY, my_l = 0.0f;
-        if (tid < nb) {
-            const int b = blo + tid;
-            const long long s0 = U * b / G, s1 = U * (b + 1) / G;
-            if (max(s0, ulo) < min(s1, uhi)) {
-                my_m = __ldcg(p.part_m + (size_t) h * G + b);
-                my_l = __ldcg(p.part_l + (size_t) h * G + b);
-            }
-        }
-        bar_consumers(); // scratch free
-        if (tid < nb) {
-            mm[tid] = my_m;
-            ll[tid] = my_l;
-        }
-        bar_consumers();
-        float M = -INFINITY;
-        for (int i = 0; i < nb; ++i) M = fmaxf(M, mm[i]);
-        if (tid < nb) ww[tid] = (mm[tid] == -INFINITY) ? 0.0f : expf(__fsub_rn(mm[tid], M));
-        bar_consumers();
-        {
-            float A = 0.0f;
-#pragma unroll
-            for (int k = 0; k < kMaxPer; ++k) {
-                const int i = part + 4 * k;
-                if (i < nb && ww[i] != 0.0f) A = __fmaf_rn(av[k], ww[i], A); // stale slots have weight 0 and are skipped
-            }
-            for (int i = part + 4 * kMaxPer; i < nb; i += 4) { // very long merges (few KV heads per GPU)
-                const float w = ww[i];
-                if (w != 0.0f) A = __fmaf_rn(__ldcg(p.part_acc + ((size_t) h * G + blo + i) * 128 + d), w, A);
-            }
-            red[part * 128 + d] = A;
-        }
-        bar_consumers();
-        if (tid < 128) {
-            float Lsum = 0.0f;
-            for (int i = 0; i < nb; ++i) Lsum = __fmaf_rn(ll[i], ww[i], Lsum);
-            const float A = __fadd_rn(__fadd_rn(red[tid], red[128 + tid]), __fadd_rn(red[256 + tid], red[384 + tid]));
-            const float o = __fdiv_rn(A, Lsum);
-            so[tid] = o;
-            p.att[(size_t) h * 128 + tid] = o;
-        }
-        bar_consumers();
-        if (warp < 2) put_group(p.att_q, h * 2 + warp, lane, so[warp * 64 + lane], so[warp * 64 + 32 + lane]);
-    }
+__device__ void combine_attn(const Shared& sh, const MegaParams& p, int l) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntask = 2 * p.Hl, G = gridDim.x;
+    int k = 0;
+    for (int t = blockIdx.x; t < ntask; t += G, ++k)
+        if ((k % kConsumerWarps) == warp) combine_task(sh, p, l, t >> 1, t & 1, lane);
 }
 
 // ---------------------------------------------------------------- consumer main
@@ -868,53 +912,72 @@ __device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
         p.prof[((size_t) blockIdx.x * (p.L + 1) + l) * kProfSlots + k] = gtime_ns();
 }
 
+template <int KV_MUL>
 __device__ void consumer(const Shared& sh, const MegaParams& p) {
-    unsigned it = 0;
-    int nbar = 0;
-    for (int l = 0; l < p.layers_run; ++l) {
-        stamp(p, l, 0);
-        // --- attention block (forward.c:254-298)
-        prologue_norm_quant(sh, p, p.att_norm + (size_t) l * p.D, l == 0);
-        stamp(p, l, 1);
-        consume_mat<0>(sh, p, ph_qkv(p, l), it, p.qkv);
-        stamp(p, l, 2);
-        grid_barrier(sh, p, nbar);
-        stamp(p, l, 3);
-        consume_attn_dispatch(sh, p, l, it);
-        stamp(p, l, 4);
-        grid_barrier(sh, p, nbar);
-        stamp(p, l, 5);
-        combine_attn(sh, p);
-        stamp(p, l, 6);
-        grid_barrier(sh, p, nbar);
-        stamp(p, l, 7);
-        prologue_load_codes(sh, p.att_q, p.Pl);
-        consume_mat<1>(sh, p, ph_o(p, l), it, p.x);
-        stamp(p, l, 8);
-        grid_barrier(sh, p, nbar);
-        stamp(p, l, 9);
-        // --- feed-forward block (forward.c:303-338)
-        prologue_norm_quant(sh, p, p.ffn_norm + (size_t) l * p.D, false);
-        stamp(p, l, 10);
-        consume_mat<2>(sh, p, ph_13(p, l), it, p.h);
-        stamp(p, l, 11);
-        grid_barrier(sh, p, nbar);
-        stamp(p, l, 12);
-        prologue_quant_global(sh, p.h, p.Hdl);
-        stamp(p, l, 13);
-        consume_mat<1>(sh, p, ph_2(p, l), it, p.x);
-        stamp(p, l, 14);
-        grid_barrier(sh, p, nbar);
-        stamp(p, l, 15);
+    // refill the OTHER arena with the sentinel for the next launch (nobody reads it during this one)
+    {
+        const unsigned per = (unsigned) ((p.flow_words / 4 + gridDim.x - 1) / gridDim.x); // 16-byte pieces per CTA
+        const unsigned a = per * blockIdx.x, b = min((unsigned) (p.flow_words / 4), a + per);
+        uint4* dst = reinterpret_cast<uint4*>(p.flow_other);
+        const uint4 s4 = make_uint4(kSent, kSent, kSent, kSent);
+#pragma unroll 1
+        for (unsigned i = a + threadIdx.x; i < b; i += kConsumerThreads) dst[i] = s4;
     }
-    stamp(p, p.L, 0);
-    // --- final norm + classifier (forward.c:344-348)
-    prologue_norm_quant(sh, p, p.out_norm, p.layers_run == 0);
-    stamp(p, p.L, 1);
-    consume_mat<0>(sh, p, ph_cls(p), it, p.logits);
-    stamp(p, p.L, 2);
+    // the residual stream starts as the dequantised embedding row (forward.c:237): every CTA
+    // contributes its slice of it to the flow vector x0
+    {
+        const int tok = p.token_dev ? *p.token_dev : p.token;
+        const uint8_t* row = p.w_emb + (size_t) tok * qw_row_bytes(p.D);
+        const int c0 = (int) ((unsigned) p.D * blockIdx.x / gridDim.x), c1 = (int) ((unsigned) p.D * (blockIdx.x + 1) / gridDim.x);
+#pragma unroll 1
+        for (int c = c0 + threadIdx.x; c < c1; c += kConsumerThreads) {
+            const uint8_t* rec = row + (size_t) (c >> 8) * QW_SG_BYTES;
+            const float sc = *reinterpret_cast<const float*>(rec + 256 + ((c >> 6) & 3) * 4);
+            stf_f32(p.flow_x0 + c, __fmul_rn((float) reinterpret_cast<const int8_t*>(rec)[c & 255], sc));
+        }
+        __threadfence();
+    }
+    unsigned it = 0;
+    const float* xprev = p.flow_x0; // residual stream entering the layer
+    const int nph = 4 * p.layers_run;
+#pragma unroll 1
+    for (int ph = 0; ph <= nph; ++ph) {
+        const int l = ph >> 2, k = ph == nph ? 4 : (ph & 3);
+        float* fl = flow_layer(p, k == 4 ? 0 : l);
+        const int lp = k == 4 ? p.L : l; // profile row
+        float* out;
+        const float* resid = nullptr;
+        stamp(p, lp, 4 * (k & 3));
+        if (k == 1) { // attention block, second half (forward.c:261-298)
+            consume_attn<KV_MUL>(sh, p, l, it);
+            combine_attn(sh, p, l);
+            stamp(p, lp, 5);
+            prologue_load_codes(sh, p, reinterpret_cast<const uint8_t*>(fl + p.o_attq), p.Pl);
+            out = fl + p.o_xa;
+            resid = xprev;
+        } else {
+            const float *src, *nw;
+            int n = p.D;
+            if (k == 0) { // forward.c:254-259
+                src = xprev; nw = p.att_norm + (size_t) l * p.D; out = fl + p.o_qkv;
+            } else if (k == 2) { // forward.c:303-318
+                src = fl + p.o_xa; nw = p.ffn_norm + (size_t) l * p.D; out = fl + p.o_h;
+            } else if (k == 3) { // forward.c:319-338
+                src = fl + p.o_h; nw = nullptr; n = p.Hdl; out = fl + p.o_xb; resid = fl + p.o_xa;
+            } else { // final norm + classifier (forward.c:344-348)
+                src = xprev; nw = p.out_norm; out = p.logits;
+            }
+            prologue_quant(sh, p, src, n, nw);
+        }
+        stamp(p, lp, 4 * (k & 3) + 2);
+        consume_mat(sh, p, p.mat[k], l, it, out, resid);
+        stamp(p, lp, 4 * (k & 3) + 3);
+        if (k == 3) xprev = fl + p.o_xb;
+    }
 }
 
+// one instantiation per GQA ratio: only the attention code of the model at hand is in the kernel
+template <int KV_MUL>
 __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int abort_flag;
@@ -940,19 +1003,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ 
         if (threadIdx.x == kConsumerThreads) producer(sh, p);
         return;
     }
-    consumer(sh, p);
+    consumer<KV_MUL>(sh, p);
+}
+
+__global__ void k_fill_u32(uint32_t* dst, size_t n, uint32_t v) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) dst[i] = v;
 }
 
 } // namespace
 
 // ---------------------------------------------------------------- host side
 static MegaState* state_of(QwenCudaCtx* c) { return reinterpret_cast<MegaState*>(c->mega); }
+static const void* decode_kernel(int kv_mul) {
+    switch (kv_mul) {
+        case 1: return (const void*) k_decode<1>;
+        case 2: return (const void*) k_decode<2>;
+        case 4: return (const void*) k_decode<4>;
+        default: return (const void*) k_decode<8>;
+    }
+}
+
+// both arenas back to "nothing written" (at create, and after an aborted launch)
+int qw_mega_reset(QwenCudaCtx* c) {
+    MegaState* st = state_of(c);
+    if (!st || !st->grid) return 0;
+    for (int s = 0; s < 2; ++s) k_fill_u32<<<592, 256, 0, c->stream>>>(reinterpret_cast<uint32_t*>(st->arena[s]), st->words, kSent);
+    QW_CUDA(cudaGetLastError());
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 int qw_mega_init(QwenCudaCtx* c) {
     MegaState* st = new MegaState();
     c->mega = st;
-    if (c->tp_size != 1) { // tensor-parallel contexts use the per-op path for now
-        c->path = 1;
+    const int kv_mul = c->KVHl > 0 ? c->Hl / c->KVHl : 0;
+    if (c->tp_size != 1 || !(kv_mul == 1 || kv_mul == 2 || kv_mul == 4 || kv_mul == 8) || kv_mul * c->KVHl != c->Hl) {
+        c->path = 1; // tensor-parallel contexts and unusual head ratios use the per-op path
         return 0;
     }
     const int amax = qw_pad_cols(std::max(c->D, std::max(c->Pl, c->Hdl)));
@@ -960,9 +1046,9 @@ int qw_mega_init(QwenCudaCtx* c) {
         qw_set_error("persistent decode kernel: a weight row (%d columns) does not fit one %d-byte ring slot", amax, kSlotBytes);
         return -1;
     }
-    if (qw_pad_cols(c->D) / 64 > kMaxGroupsPerWarpNorm * kConsumerWarps) {
+    if (qw_sg_per_row(c->D) > kRecBatch * kConsumerWarps) {
         qw_set_error("persistent decode kernel: dim %d exceeds the fused RMSNorm prologue's %d columns", c->D,
-                     kMaxGroupsPerWarpNorm * kConsumerWarps * 64);
+                     kRecBatch * kConsumerWarps * 256);
         return -1;
     }
     int dev_smem = 0, coop = 0;
@@ -980,15 +1066,14 @@ int qw_mega_init(QwenCudaCtx* c) {
     };
     // everything except the ring first, then give the ring all remaining slots
     const int xq_b = (int) qw_row_bytes(amax);
-    const int scr_b = kScrFloats * 4;
+    const int scr_b = std::max(kScrFloats, (kv_mul + 2) * 128) * 4;
     const int misc_b = 1024, bar_b = 2 * kMaxSlots * 8;
     const int fixed = ((xq_b + 127) & ~127) + ((scr_b + 127) & ~127) + ((misc_b + 127) & ~127) + ((bar_b + 127) & ~127);
     const int avail = dev_smem - fixed - 1024; // 1 KB left for static shared + driver reserve
     st->nslot = std::min(kMaxSlots, avail / kSlotBytes);
     if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(st->nslot, atoi(e)));
     if (const char* e = getenv("QWEN_MEGA_MODE")) st->dbg_mode = atoi(e);
-    if (const char* e = getenv("QWEN_MEGA_SPLIT")) st->copy_split = std::max(1, atoi(e));
-    if (getenv("QWEN_MEGA_VERBOSE")) fprintf(stderr, "[mega] nslot %d mode %d split %d smem %d\n", st->nslot, st->dbg_mode, st->copy_split, fixed);
+    if (getenv("QWEN_MEGA_VERBOSE")) fprintf(stderr, "[mega] nslot %d mode %d smem %d\n", st->nslot, st->dbg_mode, fixed);
     if (st->nslot < 2) {
         qw_set_error("persistent decode kernel: not enough shared memory for a 2-slot ring (%d bytes free)", avail);
         return -1;
@@ -999,14 +1084,14 @@ int qw_mega_init(QwenCudaCtx* c) {
     st->off_misc = take(misc_b);
     st->off_bar = take(bar_b);
     st->smem = off;
-    QW_CUDA(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
+    QW_CUDA(cudaFuncSetAttribute(decode_kernel(kv_mul), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
     int per_sm = 0;
-    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode, kThreads, st->smem));
+    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel(kv_mul), kThreads, st->smem));
     if (per_sm < 1) {
         qw_set_error("persistent decode kernel does not fit on an SM (smem %zu)", st->smem);
         return -1;
     }
-    st->grid = c->num_sms;
+    st->grid = std::min(c->num_sms, kMaxGrid);
     {
         auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
         int k = std::max(1, st->grid / 3);
@@ -1014,21 +1099,30 @@ int qw_mega_init(QwenCudaCtx* c) {
         st->perm = k;
         if (const char* e = getenv("QWEN_MEGA_PERM")) { const int v = atoi(e); if (v > 0 && gcd(v, st->grid) == 1) st->perm = v; }
     }
-    QW_CUDA(cudaMalloc((void**) &st->att_q, qw_row_bytes(c->Pl)));
-    QW_CUDA(cudaMemset(st->att_q, 0, qw_row_bytes(c->Pl))); // pad groups stay zero
-    QW_CUDA(cudaMalloc((void**) &st->part_m, (size_t) c->Hl * st->grid * 4));
-    QW_CUDA(cudaMalloc((void**) &st->part_l, (size_t) c->Hl * st->grid * 4));
-    QW_CUDA(cudaMalloc((void**) &st->part_acc, (size_t) c->Hl * st->grid * 128 * 4));
-    QW_CUDA(cudaMemset(c->bar_counter, 0, 512 * 8)); // one flag word per CTA
-    c->bar_epoch = 0;
+    // flow arena: per layer [xa D][xb D][qkv P+2K][h Hd][attq row_bytes(P)/4][partials KVH x slots x kv_mul x 132]
+    {
+        auto up4 = [](size_t w) { return (w + 3) & ~(size_t) 3; };
+        size_t o = 0;
+        st->o_xa = (int) o; o += up4(c->D);
+        st->o_xb = (int) o; o += up4(c->D);
+        st->o_qkv = (int) o; o += up4((size_t) c->Pl + 2 * c->Kl);
+        st->o_h = (int) o; o += up4(c->Hdl);
+        st->o_attq = (int) o; o += up4(qw_row_bytes(c->Pl) / 4);
+        st->part_slots = std::min(st->grid, st->grid / c->KVHl + 2);
+        st->o_part = (int) o; o += up4((size_t) c->KVHl * st->part_slots * kv_mul * kPartStride);
+        st->layer_words = o;
+        st->x0_off = o * c->L; // after the layers: the embedding row
+        st->words = o * c->L + up4(c->D);
+        for (int s = 0; s < 2; ++s) QW_CUDA(cudaMalloc((void**) &st->arena[s], st->words * 4));
+    }
     c->path = 0;
-    return 0;
+    return qw_mega_reset(c);
 }
 
 void qw_mega_free(QwenCudaCtx* c) {
     MegaState* st = state_of(c);
     if (!st) return;
-    void* bufs[] = {st->tlog, st->att_q, st->part_m, st->part_l, st->part_acc, st->prof};
+    void* bufs[] = {st->arena[0], st->arena[1], st->prof};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete st;
@@ -1046,32 +1140,54 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.S = c->S; p.kv_mul = c->Hl / c->KVHl;
     p.pos = pos; p.token = token; p.token_dev = token_dev;
     p.layers_run = (c->layers_run >= 0 && c->layers_run <= c->L) ? c->layers_run : c->L;
-    p.w_qkv = c->w_qkv; p.w_o = c->w_o; p.w_13 = c->w_13; p.w_2 = c->w_2; p.w_cls = c->w_cls; p.w_emb = c->w_emb;
-    p.s_qkv = c->w_qkv_stride; p.s_o = c->w_o_stride; p.s_13 = c->w_13_stride; p.s_2 = c->w_2_stride;
+    auto desc = [](const uint8_t* base, size_t stride, int rows, int n, int gran, int kind) {
+        int rt = kSlotBytes / (int) qw_row_bytes(n);
+        if (rt >= 2) rt &= ~1; // whole 2-row units per tile
+        if (rt < gran) rt = gran;
+        return MatDesc{base, stride, rows, n, gran, rt, kind};
+    };
+    p.mat[0] = desc(c->w_qkv, c->w_qkv_stride, c->Pl + 2 * c->Kl, c->D, 1, 0);
+    p.mat[1] = desc(c->w_o, c->w_o_stride, c->D, c->Pl, 1, 1);
+    p.mat[2] = desc(c->w_13, c->w_13_stride, 2 * c->Hdl, c->D, 2, 2);
+    p.mat[3] = desc(c->w_2, c->w_2_stride, c->D, c->Hdl, 1, 1);
+    p.mat[4] = desc(c->w_cls, 0, c->Vl, c->D, 1, 0);
+    p.w_emb = c->w_emb;
     p.att_norm = c->att_norm; p.ffn_norm = c->ffn_norm; p.out_norm = c->out_norm; p.q_norm = c->q_norm; p.k_norm = c->k_norm;
     p.rope_cos = c->rope_cos; p.rope_sin = c->rope_sin;
     p.k_cache = c->k_cache; p.v_cache = c->v_cache;
-    p.x = c->x; p.qkv = c->qkv; p.att = c->att; p.h = c->h; p.logits = c->logits;
-    p.att_q = st->att_q;
-    p.part_m = st->part_m; p.part_l = st->part_l; p.part_acc = st->part_acc;
-    p.bar = c->bar_counter; p.bar_base = c->bar_epoch;
+    p.flow = st->arena[st->launches & 1];
+    p.flow_other = st->arena[(st->launches + 1) & 1];
+    p.flow_x0 = p.flow + st->x0_off;
+    p.flow_layer_words = st->layer_words; p.flow_words = st->words;
+    p.o_xa = st->o_xa; p.o_xb = st->o_xb; p.o_qkv = st->o_qkv; p.o_h = st->o_h; p.o_attq = st->o_attq; p.o_part = st->o_part;
+    p.part_slots = st->part_slots;
+    p.att = c->att; p.logits = c->logits;
     p.err = c->err_flag;
     p.dbg_mode = st->dbg_mode;
     p.perm = st->perm;
-    p.copy_split = st->copy_split;
     p.prof = st->prof;
-    p.tlog = st->tlog;
-    p.tlog_warp = st->tlog_warp;
     p.nslot = st->nslot; p.off_xq = st->off_xq; p.off_scr = st->off_scr;
     p.off_misc = st->off_misc; p.off_bar = st->off_bar;
-    const int nbar = 6 * p.layers_run;
-    c->bar_epoch += (unsigned long long) nbar * st->grid;
     void* args[] = {&p};
-    QW_CUDA(cudaLaunchCooperativeKernel((const void*) k_decode, dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
+    // cooperative launch: the CTAs wait for each other's results, so all of them must be resident
+    QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
+    st->last_layers = p.layers_run;
+    ++st->launches;
     return 0;
 }
 
 int qw_decode_mega_launches(const QwenCudaCtx*) { return 1; }
+
+// debug: where the last persistent-kernel step left the vector `what` of the last layer it ran
+const float* qw_mega_debug_ptr(QwenCudaCtx* c, const char* what) {
+    MegaState* st = state_of(c);
+    if (!st || !st->grid || !st->launches || st->last_layers < 1) return nullptr;
+    const float* fl = st->arena[(st->launches - 1) & 1] + (size_t) (st->last_layers - 1) * st->layer_words;
+    if (what[0] == 'x' && !what[1]) return fl + st->o_xb;
+    if (what[0] == 'h' && !what[1]) return fl + st->o_h;
+    if (what[0] == 'q' && what[1] == 'k') return fl + st->o_qkv;
+    return nullptr;
+}
 
 // debug: per-CTA phase timestamps of the NEXT steps; read back with qw_mega_profile_read
 int qw_mega_profile_enable(QwenCudaCtx* c) {
@@ -1083,19 +1199,9 @@ int qw_mega_profile_enable(QwenCudaCtx* c) {
     QW_CUDA(cudaDeviceSynchronize());
     return (int) n;
 }
-int qw_mega_tlog(QwenCudaCtx* c, int warp, unsigned long long* host) {
-    MegaState* st = state_of(c);
-    if (!st || !st->grid) return -1;
-    if (!host) { // enable
-        if (!st->tlog) QW_CUDA(cudaMalloc((void**) &st->tlog, 4 * kTileLog * 8));
-        QW_CUDA(cudaMemset(st->tlog, 0, 4 * kTileLog * 8));
-        QW_CUDA(cudaDeviceSynchronize());
-        st->tlog_warp = warp;
-        return kTileLog;
-    }
-    QW_CUDA(cudaStreamSynchronize(c->stream));
-    QW_CUDA(cudaMemcpy(host, st->tlog, 4 * kTileLog * 8, cudaMemcpyDeviceToHost));
-    return kTileLog;
+int qw_mega_tlog(QwenCudaCtx*, int, unsigned long long*) {
+    qw_set_error("per-tile logging is not compiled into this build");
+    return -1;
 }
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
     MegaState* st = state_of(c);
