@@ -52,6 +52,7 @@ constexpr int kMaxGrid = 256;
 constexpr unsigned long long kTimeoutNs = 2000000000ull;
 constexpr int kProfSlots = 16;              // per layer: stamps after each phase step (CTA-local, thread 0)
 constexpr uint32_t kSent = 0x7F808080u;     // "not written yet": sNaN as fp32, contains code -128 as int8x4
+constexpr int kGroupTiles = 4;              // attention tiles the 15 warps work on together
 constexpr int kPartStride = 132;            // floats per published attention partial: acc[128], m, l, pad
 
 // one weight matrix of the step's schedule, filled on the host (no divisions left for the kernel)
@@ -68,6 +69,7 @@ struct MegaParams {
     int pos, token, layers_run;
     int perm;       // CTA -> row-block permutation multiplier (coprime to the grid)
     int dbg_mode;   // 0 normal; 1 consumers skip the GEMV math (ring throughput test)
+    int l2_ahead;   // 0: no L2 prefetch; else prefetch the next sub-phase (and this many 32 KB pieces of the classifier)
     const int* token_dev;
     MatDesc mat[5]; // 0 wq|wk|wv, 1 wo, 2 w1/w3 interleaved, 3 w2, 4 classifier
     const uint8_t* w_emb;
@@ -90,7 +92,7 @@ struct MegaState {
     int o_xa = 0, o_xb = 0, o_qkv = 0, o_h = 0, o_attq = 0, o_part = 0, part_slots = 0;
     unsigned launches = 0;
     int last_layers = 0;
-    int grid = 0, nslot = 0, dbg_mode = 0, perm = 1;
+    int grid = 0, nslot = 0, dbg_mode = 0, perm = 1, l2_ahead = 0;
     unsigned long long* prof = nullptr;
     size_t smem = 0;
     int off_xq, off_scr, off_misc, off_bar;
@@ -120,8 +122,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(0x12F0000000000000ull) // evict-first: a tile is read once
                  : "memory");
 }
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -266,14 +268,69 @@ __device__ __noinline__ int block_of_unit(unsigned unit, unsigned U, unsigned G)
     return (int) b;
 }
 
+__device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
+    if (p.prof && threadIdx.x == 0)
+        p.prof[((size_t) blockIdx.x * (p.L + 1) + l) * kProfSlots + k] = gtime_ns();
+}
+
 // ---------------------------------------------------------------- producer
+// L2 prefetch of a contiguous byte range (the hardware takes it in pieces of <= 32 KB here)
+__device__ __forceinline__ void prefetch_l2(const uint8_t* src, size_t bytes) {
+#pragma unroll 1
+    for (size_t o = 0; o < bytes; o += 32768) {
+        const uint32_t n = (uint32_t) min((size_t) 32768, bytes - o);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + o), "r"(n) : "memory");
+    }
+}
+// prefetch everything this CTA will read in sub-phase sp (5 * layer + {0 QKV, 1 attention, 2 WO, 3 W13, 4 W2};
+// 5 * layers_run = classifier): one contiguous range per matrix, one K and one V range per KV-head segment
+__device__ __noinline__ void prefetch_subphase(const MegaParams& p, int sp) {
+    const int nsp = 5 * p.layers_run;
+    if (sp > nsp) return;
+    const int l = sp / 5, k = sp == nsp ? 5 : sp % 5;
+    if (k == 1) {
+        int nc, u0, u1;
+        attn_units(p, nc, u0, u1);
+        for (int u = u0; u < u1;) {
+            const int kvh = u / nc, seg_end = min(u1, (kvh + 1) * nc);
+            const int p0 = (u - kvh * nc) * kChunk;
+            const int cnt = min(p.pos, (seg_end - kvh * nc) * kChunk) - p0;
+            if (cnt > 0) {
+                const size_t off = (((size_t) l * p.KVHl + kvh) * p.S + p0) * 128;
+                prefetch_l2(reinterpret_cast<const uint8_t*>(p.k_cache + off), (size_t) cnt * 512);
+                prefetch_l2(reinterpret_cast<const uint8_t*>(p.v_cache + off), (size_t) cnt * 512);
+            }
+            u = seg_end;
+        }
+    } else {
+        const MatDesc& m = p.mat[k == 0 ? 0 : k == 5 ? 4 : k - 1];
+        int r0, r1;
+        cta_rows(m, p.perm, r0, r1);
+        const size_t rb = qw_row_bytes(m.n);
+        size_t bytes = (size_t) (r1 - r0) * rb;
+        if (k == 5) bytes = min(bytes, (size_t) p.l2_ahead * 32768); // the classifier is far larger than L2's share
+        prefetch_l2(m.base + (k == 5 ? 0 : (size_t) l * m.stride) + (size_t) r0 * rb, bytes);
+    }
+}
+
+// The producer copies tile `it` of the schedule into shared-memory slot it % nslot as soon as the consumers
+// have released the slot (evict-first L2 hint: once in shared memory a tile is dead in L2).
+// Optional (QWEN_MEGA_L2AHEAD=1, default off): on ENTERING a sub-phase also prefetch the whole next sub-phase
+// of this CTA into L2 with cp.async.bulk.prefetch.L2. Measured on B200 (scripts/ubench/l2pf.cu,
+// handoff.cu): HBM->L2 prefetch traffic does not slow the hand-offs the way streaming into shared memory
+// does, but a bulk copy that hits L2 is no faster than one that streams from HBM -- 148 SMs x 6 copies of
+// 28 KB in flight top out at 7.5 TB/s either way -- so the ring refills no sooner and the step time does
+// not improve (2.07 ms vs 2.14 ms with the prefetch on).
 __device__ void producer(const Shared& sh, const MegaParams& p) {
     unsigned it = 0;
     const int nph = 4 * p.layers_run;
+    int sp = 0;
 #pragma unroll 1
     for (int ph = 0; ph <= nph; ++ph) {
         const int l = ph >> 2, k = ph == nph ? 4 : (ph & 3);
         if (k == 1) { // the layer's KV tiles come between QKV and WO
+            if (p.l2_ahead) prefetch_subphase(p, sp + 1);
+            ++sp;
             int nc, u0, u1;
             attn_units(p, nc, u0, u1);
 #pragma unroll 1
@@ -295,6 +352,8 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
                 }
             }
         }
+        if (p.l2_ahead) prefetch_subphase(p, sp + 1);
+        ++sp;
         const MatDesc& m = p.mat[k];
         int r0, r1;
         cta_rows(m, p.perm, r0, r1);
@@ -586,7 +645,7 @@ __device__ __forceinline__ void attn_state_reset(AttnState<HW>& st) {
     }
 }
 
-// One warp attends over `cnt` positions (K rows at Kt, V rows at Vt, 128 floats each, shared memory)
+// One warp attends over `cnt` positions (K rows 128 floats each in shared memory, V rows voff floats later)
 // for HW query heads q[j] (this lane's 4 dims of each head). Scores (forward.c:156-165): every lane
 // forms its 4-dim partial dot for PB = 32 / HW positions x HW heads = 32 values, and a butterfly
 // transpose-reduction (31 shuffles) leaves lane i with the full dot of value i = (position i / HW,
@@ -594,9 +653,11 @@ __device__ __forceinline__ void attn_state_reset(AttnState<HW>& st) {
 // the probability broadcast from its lane. No shared-memory traffic besides one LDS.128 per K row
 // and per V row, and no synchronisation with other warps.
 template <int HW>
-__device__ __forceinline__ void attn_rows(const float* Kt, const float* Vt, int cnt, const float4 (&q)[HW], AttnState<HW>& st, int lane) {
+__device__ __forceinline__ void attn_rows(const float* Ka, int cnta, const float* Kb, int cnt, int voff, const float4 (&q)[HW], AttnState<HW>& st, int lane) {
+    // rows 0 .. cnta-1 live at Ka, rows cnta .. cnt-1 at Kb (the next ring slot); V rows sit voff floats after K
     constexpr int PB = 32 / HW;
     const float inv = sqrtf(128.0f);
+    Kb -= cnta * 128;
 #pragma unroll 1
     for (int b0 = 0; b0 < cnt; b0 += PB) {
         const int nb = min(PB, cnt - b0);
@@ -604,7 +665,7 @@ __device__ __forceinline__ void attn_rows(const float* Kt, const float* Vt, int 
 #pragma unroll
         for (int pp = 0; pp < PB; ++pp) {
             const int r = b0 + min(pp, nb - 1); // rows past the end recompute a valid row (masked below)
-            const float4 kf = *reinterpret_cast<const float4*>(Kt + r * 128 + lane * 4);
+            const float4 kf = *reinterpret_cast<const float4*>((r < cnta ? Ka : Kb) + r * 128 + lane * 4);
 #pragma unroll
             for (int j = 0; j < HW; ++j) {
                 float d = __fmul_rn(q[j].x, kf.x);
@@ -651,7 +712,8 @@ __device__ __forceinline__ void attn_rows(const float* Kt, const float* Vt, int 
         for (int j = 0; j < HW; ++j) st.l[j] = __fadd_rn(st.l[j], __shfl_sync(0xffffffffu, es, j));
 #pragma unroll 2
         for (int i = 0; i < nb; ++i) { // uniform across the warp
-            const float4 vv = *reinterpret_cast<const float4*>(Vt + (b0 + i) * 128 + lane * 4);
+            const int r = b0 + i;
+            const float4 vv = *reinterpret_cast<const float4*>((r < cnta ? Ka : Kb) + voff + r * 128 + lane * 4);
 #pragma unroll
             for (int j = 0; j < HW; ++j) {
                 const float pw = __shfl_sync(0xffffffffu, e, i * HW + j);
@@ -722,6 +784,18 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
     const int wi = warp / NHG;                                   // its index among the warps of the group
     const int wn = (kConsumerWarps - hg + NHG - 1) / NHG;        // warps in the group
 
+    if (u0 == u1 && (unsigned) u0 < U && warp == 0 && lane < KV_MUL) {
+        // no tiles here (short context): if this block lies between the first and last block of a KV head,
+        // the head's combine tasks expect its (m, l)
+        const int kvh = u0 / nc, b = my_block(p.perm);
+        const int blo = block_of_unit((unsigned) (kvh * nc), U, gridDim.x), bhi = block_of_unit((unsigned) (kvh * nc + nc - 1), U, gridDim.x);
+        if (b > blo && b < bhi) {
+            float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + (b - blo)) * KV_MUL + lane) * kPartStride;
+            stf_f32(dst + 128, -INFINITY);
+            stf_f32(dst + 129, 0.0f);
+            __threadfence();
+        }
+    }
     int u = u0;
     while (u < u1) {
         const int kvh = u / nc;
@@ -753,44 +827,52 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
             }
         }
         bar_consumers();
-        // ---- this warp's share of the segment's cached positions
+        stamp(p, l, 1);
+        // ---- tiles, in groups of kGroupTiles: the warps of a head group split the cached positions of a
+        // group into equal contiguous ranges (<= 2 tiles each), so all warps work on every group at once and
+        // the ring keeps flowing (splitting the whole segment contiguously serialised the warps behind it)
         const int ntile = seg_end - u;
         const int pbase = (u - kvh * nc) * kChunk;                           // first position of the segment
         const int npos = max(0, min(p.pos, pbase + ntile * kChunk) - pbase); // cached positions in the segment
-        const int my0 = (int) ((long long) npos * wi / wn), my1 = (int) ((long long) npos * (wi + 1) / wn);
         float4 q[HW];
 #pragma unroll
         for (int j = 0; j < HW; ++j) q[j] = *reinterpret_cast<const float4*>(sq + (hg * HW + j) * 128 + lane * 4);
         AttnState<HW> st;
         attn_state_reset(st);
-        // tiles of the segment, then (t == ntile) this step's own position from shared memory, which the
-        // last warp of each head group takes -- one call site of attn_rows keeps the code small
 #pragma unroll 1
-        for (int t = 0; t <= ntile; ++t) {
-            const float *Kt, *Vt;
-            int cnt = 0;
-            unsigned slot = 0;
-            if (t < ntile) {
-                const unsigned itx = it_base + (unsigned) (u - u0 + t);
-                slot = itx % p.nslot;
+        for (int g0 = 0; g0 < ntile; g0 += kGroupTiles) {
+            const int gt = min(kGroupTiles, ntile - g0);
+            const int gn = max(0, min(npos - g0 * kChunk, gt * kChunk));      // cached positions in the group
+            const int my0 = gn * wi / wn, my1 = gn * (wi + 1) / wn;           // this warp's, relative to the group
+            const float* Ka = nullptr;
+            int cnta = 0;
+#pragma unroll 1
+            for (int t = 0; t < gt; ++t) {
+                const unsigned itx = it_base + (unsigned) (u - u0 + g0 + t);
+                const unsigned slot = itx % p.nslot;
                 mbar_wait(sh, p, sh.full + slot * 8, (itx / p.nslot) & 1, 4);
                 const int a = max(my0, t * kChunk) - t * kChunk, b = min(my1, (t + 1) * kChunk) - t * kChunk;
-                Kt = reinterpret_cast<const float*>(sh.ring + (size_t) slot * kSlotBytes) + a * 128;
-                Vt = Kt + kChunk * 128;
-                cnt = b - a;
-            } else {
-                Kt = sq + KV_MUL * 128;
-                Vt = Kt + 128;
-                cnt = (own_last && wi == wn - 1) ? 1 : 0;
-            }
-            if (cnt > 0) attn_rows<HW>(Kt, Vt, cnt, q, st, lane);
-            if (t < ntile) {
+                const float* Kt = reinterpret_cast<const float*>(sh.ring + (size_t) slot * kSlotBytes) + a * 128;
+                const bool more = my1 > (t + 1) * kChunk && t + 1 < gt; // my range continues in the next tile
+                if (b > a && more) { // first of two tiles: remember it, its slot is released below
+                    Ka = Kt;
+                    cnta = b - a;
+                    continue;
+                }
+                if (b > a) attn_rows<HW>(Ka ? Ka : Kt, Ka ? cnta : b - a, Kt, (Ka ? cnta : 0) + b - a, kChunk * 128, q, st, lane);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+                if (lane == 0) {
+                    if (Ka) mbar_arrive(sh.empty + ((itx - 1) % p.nslot) * 8);
+                    mbar_arrive(sh.empty + slot * 8);
+                }
+                Ka = nullptr;
             }
         }
+        // this step's own position, from shared memory: the last warp of each head group takes it
+        if (own_last && wi == wn - 1) attn_rows<HW>(sq + KV_MUL * 128, 1, sq + KV_MUL * 128, 1, 128, q, st, lane);
         // ---- merge the warp states pairwise through shared memory (w <- w + half keeps w % NHG)
         bar_consumers(); // sq is dead from here
+        stamp(p, l, 9);
 #pragma unroll 1
         for (int half = 8; half >= NHG; half >>= 1) {
             if (warp >= half && warp < 2 * half) attn_dump<HW>(st, sh.scr + (warp - half) * (HW * kPartStride), lane);
@@ -818,100 +900,102 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
     it = it_base + (unsigned) (u1 - u0);
 }
 
-// Combine task (head h, half hf): one warp merges the published partials of the head (online-softmax
-// merge over the CTAs that attended its KV head), divides by the sum (forward.c:60-75), writes the
-// fp32 result (debug read-back) and the Q8_0 group -- 64 codes + scale -- straight into the flow
-// vector the wo GEMV loads. Lane owns dims 64*hf + lane and 64*hf + 32 + lane. The partials are taken
-// 32 at a time (lane i polls m, l of slot i), chunks are folded with a running maximum.
-__device__ __noinline__ void combine_task(const Shared& sh, const MegaParams& p, int l, int h, int hf, int lane) {
+// Combine (CTA-wide): task t = (head h, half hf) merges the published partials of the head (online-
+// softmax merge over the CTAs that attended its KV head), divides by the sum (forward.c:60-75), writes
+// the fp32 result (debug read-back) and the Q8_0 group -- 64 codes + scale -- straight into the flow
+// vector the wo GEMV loads. Task t runs on CTA t % grid with ALL its warps: thread (dim = tid & 63,
+// slot group = tid >> 6) takes slots sg, sg + 7, ...; every load of the task is in flight at once, so
+// the task costs one L2 round trip plus a shared-memory reduction. Every block between the first and
+// last block of a KV head publishes (m, l) -- blocks without tiles publish (-inf, 0) -- so no slot of
+// the range stays unwritten.
+__device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams& p, int l) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntask = 2 * p.Hl;
+    const unsigned G = gridDim.x;
     float* fl = flow_layer(p, l);
+    float* mm = sh.scr;        // [<= kMaxGrid] slot maxima, then slot weights
+    float* ll = sh.scr + 256;  // [<= kMaxGrid] slot sums
+    float* red = sh.scr + 512; // [7][64] partial outputs per slot group
     const int nc = p.pos / kChunk + 1;
-    const unsigned U = (unsigned) (p.KVHl * nc), G = gridDim.x;
-    const int kvh = h / p.kv_mul, j = h % p.kv_mul;
-    const unsigned ulo = (unsigned) (kvh * nc), uhi = ulo + nc;
-    const int blo = block_of_unit(ulo, U, G), bhi = block_of_unit(uhi - 1, U, G);
-    const int nb = bhi - blo + 1;
-    const float* part = fl + p.o_part + ((size_t) kvh * p.part_slots * p.kv_mul + j) * kPartStride;
-    const size_t sstride = (size_t) p.kv_mul * kPartStride; // between slots
-    const int d0 = hf * 64 + lane;
-    float M = -INFINITY, Ls = 0.0f, A0 = 0.0f, A1 = 0.0f;
+    const unsigned U = (unsigned) (p.KVHl * nc);
 #pragma unroll 1
-    for (int base = 0; base < nb; base += 32) {
-        const int n = min(32, nb - base);
-        float m = -INFINITY, lsum = 0.0f;
-        if (lane < n) {
-            const unsigned b = (unsigned) (blo + base + lane);
-            if (U * b / G < U * (b + 1) / G) { // the block has tiles (of this KV head, or it would not lie inside)
-                m = poll1(sh, p, part + (base + lane) * sstride + 128, 14);
-                lsum = poll1(sh, p, part + (base + lane) * sstride + 129, 14);
-            }
-        }
-        const float Mn = fmaxf(M, warp_max(m));
-        const float resc = (M == -INFINITY) ? 0.0f : expf(__fsub_rn(M, Mn));
-        const float w = (m == -INFINITY) ? 0.0f : expf(__fsub_rn(m, Mn)); // weight of this lane's slot
-        Ls = __fmaf_rn(Ls, resc, warp_sum(__fmul_rn(lsum, w)));
-        A0 = __fmul_rn(A0, resc);
-        A1 = __fmul_rn(A1, resc);
-        M = Mn;
-#pragma unroll 1
-        for (int i0 = 0; i0 < n; i0 += 4) {
-            float a0[4], a1[4], wk[4];
+    for (int t = blockIdx.x; t < ntask; t += G) {
+        const int h = t >> 1, hf = t & 1, kvh = h / p.kv_mul;
+        const unsigned ulo = (unsigned) (kvh * nc);
+        const int blo = block_of_unit(ulo, U, G), nb = block_of_unit(ulo + nc - 1, U, G) - blo + 1;
+        const float* part = fl + p.o_part + ((size_t) kvh * p.part_slots * p.kv_mul + h % p.kv_mul) * kPartStride;
+        const size_t ss = (size_t) p.kv_mul * kPartStride; // between slots
+        const int d = hf * 64 + (tid & 63), sg = tid >> 6;
+        bar_consumers(); // scratch free (attention merge / previous task)
+        float a[3];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                wk[k] = __shfl_sync(0xffffffffu, w, (i0 + k) & 31);
-                a0[k] = a1[k] = 0.0f;
-                if (i0 + k < n && wk[k] != 0.0f) {
-                    a0[k] = __uint_as_float(ldf_u32(part + (base + i0 + k) * sstride + d0));
-                    a1[k] = __uint_as_float(ldf_u32(part + (base + i0 + k) * sstride + d0 + 32));
+        for (int k = 0; k < 3; ++k) { // speculative: issued before the weights are known
+            const int i = sg + 7 * k;
+            a[k] = (sg < 7 && i < nb) ? __uint_as_float(ldf_u32(part + i * ss + d)) : 0.0f;
+        }
+        if (tid < nb) {
+            mm[tid] = poll1(sh, p, part + tid * ss + 128, 14);
+            ll[tid] = poll1(sh, p, part + tid * ss + 129, 14);
+        }
+        bar_consumers();
+        float M = -INFINITY;
+#pragma unroll 1
+        for (int i = 0; i < nb; ++i) M = fmaxf(M, mm[i]);
+        if (sg < 7) {
+            float A = 0.0f;
+#pragma unroll 1
+            for (int i0 = sg; i0 < nb; i0 += 21) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = i0 + 7 * k;
+                    if (i >= nb) continue;
+                    const float m = mm[i];
+                    if (m == -INFINITY) continue; // nothing attended there: its accumulator is not even written
+                    float v = i0 == sg ? a[k] : __uint_as_float(ldf_u32(part + i * ss + d));
+                    if (__float_as_uint(v) == kSent) v = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + i * ss + d, 14));
+                    A = __fmaf_rn(v, expf(__fsub_rn(m, M)), A);
                 }
             }
+            red[sg * 64 + (tid & 63)] = A;
+        }
+        bar_consumers();
+        if (warp == 0) {
+            float A0 = 0.0f, A1 = 0.0f, Ls = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (i0 + k < n && wk[k] != 0.0f) {
-                    if (__float_as_uint(a0[k]) == kSent) a0[k] = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + (base + i0 + k) * sstride + d0, 14));
-                    if (__float_as_uint(a1[k]) == kSent) a1[k] = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + (base + i0 + k) * sstride + d0 + 32, 14));
-                    A0 = __fmaf_rn(a0[k], wk[k], A0);
-                    A1 = __fmaf_rn(a1[k], wk[k], A1);
-                }
+            for (int s7 = 0; s7 < 7; ++s7) {
+                A0 = __fadd_rn(A0, red[s7 * 64 + lane]);
+                A1 = __fadd_rn(A1, red[s7 * 64 + 32 + lane]);
             }
+#pragma unroll 1
+            for (int i = lane; i < nb; i += 32)
+                if (mm[i] != -INFINITY) Ls = __fmaf_rn(ll[i], expf(__fsub_rn(mm[i], M)), Ls);
+            Ls = warp_sum(Ls);
+            const float o0 = __fdiv_rn(A0, Ls), o1 = __fdiv_rn(A1, Ls);
+            const int d0 = hf * 64 + lane;
+            p.att[(size_t) h * 128 + d0] = o0;
+            p.att[(size_t) h * 128 + d0 + 32] = o1;
+            // quantise the group (q8.c:5-30) and store packed code words + scale
+            const float scale = q8_scale(warp_max(fmaxf(fabsf(o0), fabsf(o1))));
+            const uint32_t c0 = (uint32_t) (q8_code(o0, scale) & 0xff), c1 = (uint32_t) (q8_code(o1, scale) & 0xff);
+            uint32_t w0 = c0, w1 = c1;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                w0 |= __shfl_down_sync(0xffffffffu, c0, k) << (8 * k);
+                w1 |= __shfl_down_sync(0xffffffffu, c1, k) << (8 * k);
+            }
+            const int g = h * 2 + hf;
+            uint8_t* rec = reinterpret_cast<uint8_t*>(fl + p.o_attq) + (size_t) (g >> 2) * QW_SG_BYTES;
+            if ((lane & 3) == 0) {
+                stf_u32(rec + (g & 3) * 64 + lane, w0);
+                stf_u32(rec + (g & 3) * 64 + 32 + lane, w1);
+            }
+            if (lane == 0) stf_f32(reinterpret_cast<float*>(rec + 256 + (g & 3) * 4), scale);
+            __threadfence(); // flush (see consume_mat)
         }
     }
-    const float o0 = __fdiv_rn(A0, Ls), o1 = __fdiv_rn(A1, Ls);
-    p.att[(size_t) h * 128 + d0] = o0;
-    p.att[(size_t) h * 128 + d0 + 32] = o1;
-    // quantise the group (q8.c:5-30) and store packed code words + scale
-    const float scale = q8_scale(warp_max(fmaxf(fabsf(o0), fabsf(o1))));
-    const uint32_t c0 = (uint32_t) (q8_code(o0, scale) & 0xff), c1 = (uint32_t) (q8_code(o1, scale) & 0xff);
-    uint32_t w0 = c0, w1 = c1;
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-        w0 |= __shfl_down_sync(0xffffffffu, c0, k) << (8 * k);
-        w1 |= __shfl_down_sync(0xffffffffu, c1, k) << (8 * k);
-    }
-    const int g = h * 2 + hf;
-    uint8_t* rec = reinterpret_cast<uint8_t*>(fl + p.o_attq) + (size_t) (g >> 2) * QW_SG_BYTES;
-    if ((lane & 3) == 0) {
-        stf_u32(rec + (g & 3) * 64 + lane, w0);
-        stf_u32(rec + (g & 3) * 64 + 32 + lane, w1);
-    }
-    if (lane == 0) stf_f32(reinterpret_cast<float*>(rec + 256 + (g & 3) * 4), scale);
-    __threadfence(); // flush (see consume_mat)
-}
-
-__device__ void combine_attn(const Shared& sh, const MegaParams& p, int l) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ntask = 2 * p.Hl, G = gridDim.x;
-    int k = 0;
-    for (int t = blockIdx.x; t < ntask; t += G, ++k)
-        if ((k % kConsumerWarps) == warp) combine_task(sh, p, l, t >> 1, t & 1, lane);
 }
 
 // ---------------------------------------------------------------- consumer main
-__device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
-    if (p.prof && threadIdx.x == 0)
-        p.prof[((size_t) blockIdx.x * (p.L + 1) + l) * kProfSlots + k] = gtime_ns();
-}
-
 template <int KV_MUL>
 __device__ void consumer(const Shared& sh, const MegaParams& p) {
     // refill the OTHER arena with the sentinel for the next launch (nobody reads it during this one)
@@ -950,6 +1034,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
         stamp(p, lp, 4 * (k & 3));
         if (k == 1) { // attention block, second half (forward.c:261-298)
             consume_attn<KV_MUL>(sh, p, l, it);
+            stamp(p, lp, 13);
             combine_attn(sh, p, l);
             stamp(p, lp, 5);
             prologue_load_codes(sh, p, reinterpret_cast<const uint8_t*>(fl + p.o_attq), p.Pl);
@@ -1073,6 +1158,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     st->nslot = std::min(kMaxSlots, avail / kSlotBytes);
     if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(st->nslot, atoi(e)));
     if (const char* e = getenv("QWEN_MEGA_MODE")) st->dbg_mode = atoi(e);
+    if (const char* e = getenv("QWEN_MEGA_L2AHEAD")) st->l2_ahead = std::max(0, atoi(e));
     if (getenv("QWEN_MEGA_VERBOSE")) fprintf(stderr, "[mega] nslot %d mode %d smem %d\n", st->nslot, st->dbg_mode, fixed);
     if (st->nslot < 2) {
         qw_set_error("persistent decode kernel: not enough shared memory for a 2-slot ring (%d bytes free)", avail);
@@ -1164,6 +1250,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.att = c->att; p.logits = c->logits;
     p.err = c->err_flag;
     p.dbg_mode = st->dbg_mode;
+    p.l2_ahead = st->l2_ahead;
     p.perm = st->perm;
     p.prof = st->prof;
     p.nslot = st->nslot; p.off_xq = st->off_xq; p.off_scr = st->off_scr;

@@ -192,11 +192,18 @@ k_fanin_load(uint32_t* arena, unsigned* ctr, const uint8_t* big, size_t big_byte
         const unsigned tb = ((slack >> 24) & 0xff) ? ((slack >> 24) & 0xff) * 1024u : 28672u; // bytes per copy
         for (unsigned it = 0; !done; ++it) {
             const unsigned slot = it % depth, par = (it / depth) & 1;
-            if (it >= depth) { // wait for the previous copy into this slot
+            if (!(slack & 0x20000) && it >= depth) { // wait for the previous copy into this slot
                 uint32_t ok = 0;
                 while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(s_u32(&bars[slot])), "r"(par ^ 1) : "memory");
             }
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&bars[slot])), "r"(tb) : "memory");
+            if (!(slack & 0x20000)) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&bars[slot])), "r"(tb) : "memory");
+            if (slack & 0x20000) { // L2 prefetch only: nothing crosses the crossbar to this SM; paced by the clock
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t) (it % (per / 28672)) * 28672), "r"(tb) : "memory");
+                const unsigned long long tw = gtime() + (unsigned long long) ((slack >> 20) & 7) * 100; // pace: depth field x 100 ns per copy
+                while (gtime() < tw) {}
+                tiles += tb;
+                continue;
+            }
             if (slack & 0x10000)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(s_u32(ring + slot * 28672)),
                              "l"(src + (size_t) (it % (per / 28672)) * 28672), "r"(tb), "r"(s_u32(&bars[slot])), "l"(0x12F0000000000000ull) : "memory");
@@ -321,13 +328,11 @@ int main() {
         cudaMalloc(&out2, 296 * 8);
         for (int D : {2560}) {
             char nm[96];
-            for (int depth : {1, 2, 3, 6})
-                for (int kb : {4, 8, 14, 28}) {
-                    snprintf(nm, sizeof nm, "sentinel spin, stream depth %d x %2d KB", depth, kb);
-                    run_load<0>(nm, buf, ctr, big, big_bytes, out2, sink, D, (depth << 20) | (kb << 24));
-                }
-            run_load<1>("counter then load, depth 2 x 14 KB", buf, ctr, big, big_bytes, out2, sink, D, (2 << 20) | (14 << 24));
-            run_load<1>("counter then load, depth 1 x 28 KB", buf, ctr, big, big_bytes, out2, sink, D, (1 << 20) | (28 << 24));
+            for (int pace : {7, 6, 5, 4, 3}) {
+                snprintf(nm, sizeof nm, "sentinel spin, L2 prefetch 28 KB / %d00 ns", pace);
+                run_load<0>(nm, buf, ctr, big, big_bytes, out2, sink, D, 0x20000 | (pace << 20) | (28 << 24));
+            }
+            run_load<0>("sentinel spin, stream depth 2 x 28 KB", buf, ctr, big, big_bytes, out2, sink, D, (2 << 20) | (28 << 24));
         }
     }
     return 0;
