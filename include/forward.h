@@ -67,6 +67,17 @@ void attention(Model* m, int layer, int pos);
  */
 float* forward(Model* m, int token, int pos);
 
+/*
+ * EXTENSION of the B200 build (the reference has no such function): the prompt
+ * loop of src/completion.c:57-66 -- forward() once per prompt token, all logits
+ * but the last discarded -- as one call. Runs n tokens at positions pos .. pos+n-1
+ * through the layers together (tensor-core int8 GEMMs), writes their KV slots and
+ * returns m->state.logits holding the LAST token's logits; NULL on error.
+ * A generation loop switches to it by replacing its prompt loop with one call
+ * (INTEGRATION.md); callers that never use it are unaffected.
+ */
+float* forward_prefill(Model* m, const int* tokens, int n, int pos);
+
 #ifdef __cplusplus
 }
 #endif

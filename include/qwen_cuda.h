@@ -97,6 +97,11 @@ int qwen_cuda_forward(QwenCudaCtx* ctx, int token, int pos, float* logits_host);
 int qwen_cuda_forward_async(QwenCudaCtx* ctx, int token, int pos);
 /* Copy the device logits of the last step to the host and wait. */
 int qwen_cuda_logits_to_host(QwenCudaCtx* ctx, float* logits_host);
+/* Prompt prefill: n tokens at positions pos0 .. pos0 + n - 1 in one pass (tcgen05 int8 GEMMs + batched
+ * small ops + causal attention), KV cache rows written for all of them; logits_host (may be NULL) receives
+ * the LAST token's logits. Same result as n forward() calls (reference: src/completion.c:57-66, which
+ * discards all but the last logits). */
+int qwen_cuda_prefill(QwenCudaCtx* ctx, const int* tokens, int n, int pos0, float* logits_host);
 /* Greedy chain entirely on the device: n steps starting at (first_token, pos0); step i
  * feeds the argmax (lowest index on ties) of step i-1. out_tokens_host[n] receives the
  * n argmax tokens. Stands behind the completion loop's forward+sample pair when the

@@ -73,6 +73,9 @@ class QwenLib:
         L.model_cuda_ctx.argtypes = [C.POINTER(Model)]
         L.forward.restype = c_float_p
         L.forward.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
+        L.forward_prefill.restype = c_float_p
+        L.forward_prefill.argtypes = [C.POINTER(Model), C.POINTER(C.c_int), C.c_int, C.c_int]
+        L.qwen_cuda_prefill.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, c_float_p]
         L.attention.argtypes = [C.POINTER(Model), C.c_int, C.c_int]
         L.attention.restype = None
         L.rmsnorm.argtypes = [c_float_p, c_float_p, c_float_p, C.c_int]
@@ -202,6 +205,19 @@ class B200Model:
         if not ptr:
             raise RuntimeError(f"forward failed: {self.ql.err()}")
         return np.ctypeslib.as_array(ptr, shape=(self.p.vocab_size,)).copy()
+
+    def forward_prefill(self, tokens, pos: int) -> np.ndarray:
+        """forward_prefill(): the prompt tokens at positions pos.. in one pass; logits of the last token."""
+        arr = (C.c_int * len(tokens))(*[int(t) for t in tokens])
+        ptr = self.ql.lib.forward_prefill(self.m, arr, len(tokens), pos)
+        if not ptr:
+            raise RuntimeError(f"forward_prefill failed: {self.ql.err()}")
+        return np.ctypeslib.as_array(ptr, shape=(self.p.vocab_size,)).copy()
+
+    def prefill_nocopy(self, tokens, pos: int) -> bool:
+        """Prefill without the logits copy (device-side timing)."""
+        arr = (C.c_int * len(tokens))(*[int(t) for t in tokens])
+        return self.ql.lib.qwen_cuda_prefill(self.ctx, arr, len(tokens), pos, None) == 0
 
     def forward_nocopy(self, token: int, pos: int):
         """forward() exactly as a C caller sees it: returns the pinned logits pointer."""

@@ -1,0 +1,104 @@
+// attn_core.cuh -- the per-warp online-softmax attention step shared by the persistent decode kernel
+// (decode_mega.cu) and the prefill attention kernel (prefill.cu). Reference: src/forward.c:141-195.
+#pragma once
+
+#include "common.cuh"
+
+// Online-softmax state of one warp for HW query heads: lane owns output dims 4*lane .. 4*lane+3 of
+// every head; m and l are kept per head in every lane (identical across the warp).
+template <int HW>
+struct AttnState {
+    float4 acc[HW];
+    float m[HW], l[HW];
+};
+template <int HW>
+__device__ __forceinline__ void attn_state_reset(AttnState<HW>& st) {
+#pragma unroll
+    for (int j = 0; j < HW; ++j) {
+        st.acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        st.m[j] = -INFINITY;
+        st.l[j] = 0.0f;
+    }
+}
+
+// One warp attends over `cnt` positions (K rows 128 floats each in shared memory, V rows voff floats later)
+// for HW query heads q[j] (this lane's 4 dims of each head). Scores (forward.c:156-165): every lane
+// forms its 4-dim partial dot for PB = 32 / HW positions x HW heads = 32 values, and a butterfly
+// transpose-reduction (31 shuffles) leaves lane i with the full dot of value i = (position i / HW,
+// head i % HW). Softmax statistics per head by shuffles over the lanes of that head, then P.V with
+// the probability broadcast from its lane. No shared-memory traffic besides one LDS.128 per K row
+// and per V row, and no synchronisation with other warps.
+template <int HW>
+__device__ __forceinline__ void attn_rows(const float* Ka, int cnta, const float* Kb, int cnt, int voff, const float4 (&q)[HW], AttnState<HW>& st, int lane) {
+    // rows 0 .. cnta-1 live at Ka, rows cnta .. cnt-1 at Kb (the next ring slot); V rows sit voff floats after K
+    constexpr int PB = 32 / HW;
+    const float inv = sqrtf(128.0f);
+    Kb -= cnta * 128;
+#pragma unroll 1
+    for (int b0 = 0; b0 < cnt; b0 += PB) {
+        const int nb = min(PB, cnt - b0);
+        float v[32];
+#pragma unroll
+        for (int pp = 0; pp < PB; ++pp) {
+            const int r = b0 + min(pp, nb - 1); // rows past the end recompute a valid row (masked below)
+            const float4 kf = *reinterpret_cast<const float4*>((r < cnta ? Ka : Kb) + r * 128 + lane * 4);
+#pragma unroll
+            for (int j = 0; j < HW; ++j) {
+                float d = __fmul_rn(q[j].x, kf.x);
+                d = __fmaf_rn(q[j].y, kf.y, d);
+                d = __fmaf_rn(q[j].z, kf.z, d);
+                d = __fmaf_rn(q[j].w, kf.w, d);
+                v[pp * HW + j] = d;
+            }
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const bool hi = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                const float send = hi ? v[i] : v[i + s];
+                const float keep = hi ? v[i + s] : v[i];
+                v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, s));
+            }
+        }
+        const int pp = lane / HW;
+        const float sc = pp < nb ? __fdiv_rn(v[0], inv) : -INFINITY; // score / sqrtf(head_dim)
+        float bm = sc;
+#pragma unroll
+        for (int o = HW; o < 32; o <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        // every lane learns the block max of every head (lane j holds head j's)
+        float e = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HW; ++j) {
+            const float bmj = __shfl_sync(0xffffffffu, bm, j);
+            const float m_new = fmaxf(st.m[j], bmj);
+            const float scl = (st.m[j] == -INFINITY) ? 0.0f : expf(__fsub_rn(st.m[j], m_new));
+            if ((lane % HW) == j) e = pp < nb ? expf(__fsub_rn(sc, m_new)) : 0.0f;
+            st.m[j] = m_new;
+            st.l[j] = __fmul_rn(st.l[j], scl);
+            st.acc[j].x = __fmul_rn(st.acc[j].x, scl);
+            st.acc[j].y = __fmul_rn(st.acc[j].y, scl);
+            st.acc[j].z = __fmul_rn(st.acc[j].z, scl);
+            st.acc[j].w = __fmul_rn(st.acc[j].w, scl);
+        }
+        float es = e;
+#pragma unroll
+        for (int o = HW; o < 32; o <<= 1) es = __fadd_rn(es, __shfl_xor_sync(0xffffffffu, es, o));
+#pragma unroll
+        for (int j = 0; j < HW; ++j) st.l[j] = __fadd_rn(st.l[j], __shfl_sync(0xffffffffu, es, j));
+#pragma unroll 2
+        for (int i = 0; i < nb; ++i) { // uniform across the warp
+            const int r = b0 + i;
+            const float4 vv = *reinterpret_cast<const float4*>((r < cnta ? Ka : Kb) + voff + r * 128 + lane * 4);
+#pragma unroll
+            for (int j = 0; j < HW; ++j) {
+                const float pw = __shfl_sync(0xffffffffu, e, i * HW + j);
+                st.acc[j].x = __fmaf_rn(pw, vv.x, st.acc[j].x);
+                st.acc[j].y = __fmaf_rn(pw, vv.y, st.acc[j].y);
+                st.acc[j].z = __fmaf_rn(pw, vv.z, st.acc[j].z);
+                st.acc[j].w = __fmaf_rn(pw, vv.w, st.acc[j].w);
+            }
+        }
+    }
+}
+

@@ -159,6 +159,7 @@ struct QwenCudaCtx {
     void* nccl_comm;  // tensor-parallel communicator (tp_nccl.cu), NULL when tp_size == 1
     float* logits_all; // [V] gathered logits on tensor-parallel contexts
     void* mega;       // persistent-kernel state (decode_mega.cu)
+    void* prefill;    // prefill activation buffers (prefill.cu), allocated on first use
     int layers_run;   // debug: run only the first n layers (-1 = all)
     float* logits_pinned; // optional pinned bounce buffer
     size_t bytes_weights, bytes_kv;
@@ -176,6 +177,8 @@ void launch_repack(const int8_t* src_q, const float* src_s, int src_n, int col0,
 int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos);
 int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos);
 int qw_mega_init(QwenCudaCtx* c);
+int qw_prefill(QwenCudaCtx* c, const int* tokens_host, int n, int pos0);
+void qw_prefill_free(QwenCudaCtx* c);
 void qw_mega_free(QwenCudaCtx* c);
 int qw_tp_allreduce(QwenCudaCtx* c, float* buf, size_t n);
 int qw_tp_allgather(QwenCudaCtx* c, const float* src, float* dst, size_t n_per_rank);

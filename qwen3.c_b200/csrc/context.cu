@@ -207,6 +207,7 @@ extern "C" void qwen_cuda_destroy(QwenCudaCtx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     qw_mega_free(c);
+    qw_prefill_free(c);
     qw_tp_free(c);
     if (c->logits_all) cudaFree(c->logits_all);
     if (c->w_emb != c->w_cls) cudaFree(c->w_emb);
@@ -313,6 +314,15 @@ extern "C" int qwen_cuda_forward(QwenCudaCtx* c, int token, int pos, float* logi
     QW_CUDA(cudaSetDevice(c->device));
     if (int rc = step(c, token, nullptr, pos)) return rc;
     return qwen_cuda_logits_to_host(c, logits_host);
+}
+
+// Stands behind the prompt loop of the generation code (reference: src/completion.c:57-66 calls forward()
+// once per prompt token and keeps only the last logits): n tokens at positions pos0 .. pos0 + n - 1.
+extern "C" int qwen_cuda_prefill(QwenCudaCtx* c, const int* tokens, int n, int pos0, float* logits_host) {
+    if (!c || !tokens) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    if (int rc = qw_prefill(c, tokens, n, pos0)) return rc;
+    return logits_host ? qwen_cuda_logits_to_host(c, logits_host) : 0;
 }
 
 extern "C" int qwen_cuda_decode_greedy(QwenCudaCtx* c, int first_token, int pos0, int n, int* out_tokens_host) {

@@ -87,3 +87,14 @@ float* forward(Model* m, int token, int pos) {
     }
     return m->state.logits;
 }
+
+/* Extension (no reference counterpart; see include/forward.h): the prompt loop of
+ * src/completion.c:57-66 as one call. */
+float* forward_prefill(Model* m, const int* tokens, int n, int pos) {
+    const int rc = qwen_cuda_prefill(model_cuda_ctx(m), tokens, n, pos, m->state.logits);
+    if (rc) {
+        report("forward_prefill", rc);
+        return NULL;
+    }
+    return m->state.logits;
+}

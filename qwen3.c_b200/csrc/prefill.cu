@@ -1,0 +1,303 @@
+// prefill.cu -- prompt prefill: T tokens through the layer loop at once.
+//
+// The reference has no prefill: completion.c:57-66 calls forward() once per prompt token and throws
+// the logits of all but the last away. Here the same per-token arithmetic (src/forward.c:225-350) is
+// applied to a chunk of T tokens together, so every weight matrix is read once per chunk instead of
+// once per token and the seven projections become dense int8 contractions on the tcgen05 tensor cores
+// (prefill_gemm.cu: exact int32 group dots, the reference's ((float) dot * ws) * xs terms folded in group
+// order -- bit-identical to the reference matmul of each token). Between the GEMMs sit batched versions
+// of the small ops -- RMSNorm + Q8_0 quantise, per-head q/k norm + RoPE + KV-cache write, causal GQA
+// attention, SwiGLU, residual add -- each the reference's formula per element. The KV cache is written in
+// the decode kernel's layout, so decoding continues from the prefilled cache with the persistent kernel.
+// Only the last token's logits are produced (the reference discards the others).
+//
+// Chunks of kChunkTokens tokens bound the activation memory; chunk c attends over the cache rows of the
+// earlier chunks plus its own causal part.
+#include <algorithm>
+
+#include "attn_core.cuh"
+#include "common.cuh"
+
+int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float* out, int32_t* dots, int d, int n, int T,
+                    int Tpad, int* err_dev, cudaStream_t st, float* ms_out);
+
+namespace {
+
+constexpr int kChunkTokens = 512;
+
+struct PrefillBufs {
+    int cap = 0;          // tokens the buffers hold
+    int* tokens = nullptr;
+    float *x = nullptr, *xb = nullptr, *qkv = nullptr, *q = nullptr, *att = nullptr, *h13 = nullptr;
+    int8_t* q8 = nullptr; // [cap][maxn] activation codes of the GEMM at hand (row pitch = its n)
+    float* xsT = nullptr; // [maxn / 64][cap] activation scales, transposed for the GEMM epilogue
+    int* err = nullptr;
+};
+
+// dequantised embedding rows (forward.c:237): grid T
+__global__ void k_embed_rows(float* __restrict__ x, const uint8_t* __restrict__ w_emb, const int* __restrict__ tokens, int D) {
+    const int tok = tokens[blockIdx.x];
+    const uint8_t* row = w_emb + (size_t) tok * qw_row_bytes(D);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        const uint8_t* rec = row + (size_t) (c >> 8) * QW_SG_BYTES;
+        const float sc = *reinterpret_cast<const float*>(rec + 256 + ((c >> 6) & 3) * 4);
+        x[(size_t) blockIdx.x * D + c] = __fmul_rn((float) reinterpret_cast<const int8_t*>(rec)[c & 255], sc);
+    }
+}
+
+// One block per token: optional RMSNorm (forward.c:12-28; w == nullptr: none), optional SwiGLU over
+// interleaved (w1, w3) pairs (forward.c:122-139; src then has 2n values per token), then the Q8_0
+// quantiser (q8.c:5-30) with the reference's exact arithmetic. Codes go to q8[t][n], scales transposed to
+// xsT[g][Tpad]. 256 threads; warp w handles groups w, w + 8, ...
+__global__ void __launch_bounds__(256)
+k_prep_quant(const float* __restrict__ src, const float* __restrict__ w, int8_t* __restrict__ q8, float* __restrict__ xsT,
+             int n, int Tpad, int swiglu) {
+    __shared__ float red[8];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* s = src + (size_t) t * (swiglu ? 2 * n : n);
+    float r = 1.0f;
+    if (w) {
+        float ss = 0.0f;
+        for (int i = tid; i < n; i += 256) ss = __fmaf_rn(s[i], s[i], ss);
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot = __fadd_rn(tot, red[i]);
+        r = rms_rscale(tot, n);
+    }
+    for (int g = warp; g < n / 64; g += 8) {
+        float a, b;
+        const int i0 = g * 64 + lane, i1 = i0 + 32;
+        if (swiglu) {
+            a = __fmul_rn(silu_ref(s[2 * i0]), s[2 * i0 + 1]);
+            b = __fmul_rn(silu_ref(s[2 * i1]), s[2 * i1 + 1]);
+        } else if (w) {
+            a = __fmul_rn(w[i0], __fmul_rn(r, s[i0]));
+            b = __fmul_rn(w[i1], __fmul_rn(r, s[i1]));
+        } else {
+            a = s[i0];
+            b = s[i1];
+        }
+        const float scale = q8_scale(warp_max(fmaxf(fabsf(a), fabsf(b))));
+        q8[(size_t) t * n + i0] = (int8_t) q8_code(a, scale);
+        q8[(size_t) t * n + i1] = (int8_t) q8_code(b, scale);
+        if (lane == 0) xsT[(size_t) g * Tpad + t] = scale;
+    }
+}
+
+// per (token, head): q/k RMSNorm + RoPE at position pos0 + t, K and V written into the cache
+// (forward.c:261-280, 244-248). grid (T, Hl + 2 KVHl), 128 threads.
+__global__ void __launch_bounds__(128)
+k_qkv_post_rows(const float* __restrict__ qkv, float* __restrict__ q_out, float* __restrict__ k_layer, float* __restrict__ v_layer,
+                const float* __restrict__ gq, const float* __restrict__ gk, const float* __restrict__ rope_cos,
+                const float* __restrict__ rope_sin, int Hl, int KVHl, int S, int pos0) {
+    __shared__ float y[128];
+    __shared__ float red[4];
+    const int t = blockIdx.x, b = blockIdx.y, i = threadIdx.x, pos = pos0 + t;
+    const int width = (Hl + 2 * KVHl) * 128;
+    const float v = qkv[(size_t) t * width + (size_t) b * 128 + i];
+    if (b >= Hl + KVHl) { // V: stored raw
+        v_layer[((size_t) (b - Hl - KVHl) * S + pos) * 128 + i] = v;
+        return;
+    }
+    float ss = warp_sum(__fmul_rn(v, v));
+    if ((i & 31) == 0) red[i >> 5] = ss;
+    __syncthreads();
+    ss = __fadd_rn(__fadd_rn(red[0], red[1]), __fadd_rn(red[2], red[3]));
+    const float r = rms_rscale(ss, 128);
+    const float* g = (b < Hl) ? gq : gk;
+    y[i] = __fmul_rn(g[i], __fmul_rn(r, v));
+    __syncthreads();
+    const int j = i & 63;
+    const float c = rope_cos[(size_t) pos * 64 + j], s = rope_sin[(size_t) pos * 64 + j];
+    const float a = y[j], bb = y[j + 64];
+    const float o = (i < 64) ? __fsub_rn(__fmul_rn(a, c), __fmul_rn(bb, s)) : __fadd_rn(__fmul_rn(a, s), __fmul_rn(bb, c));
+    if (b < Hl)
+        q_out[(size_t) t * Hl * 128 + (size_t) b * 128 + i] = o;
+    else
+        k_layer[((size_t) (b - Hl) * S + pos) * 128 + i] = o;
+}
+
+// Causal GQA attention for a chunk (forward.c:141-195 per token). grid (ceil(T / 8), KVHl, NHG), 256 threads:
+// warp w = query token 8 * blockIdx.x + w with the HW query heads of head group blockIdx.z; the 8 tokens
+// share K/V tiles of 32 positions staged in shared memory; each warp runs the decode kernel's online-softmax
+// step (attn_core.cuh) over the positions it may see (0 .. pos0 + t).
+template <int KV_MUL>
+__global__ void __launch_bounds__(256)
+k_attn_prefill(const float* __restrict__ q, const float* __restrict__ k_layer, const float* __restrict__ v_layer,
+               float* __restrict__ out, int Hl, int S, int pos0, int T) {
+    constexpr int HW = KV_MUL < 4 ? KV_MUL : 4;
+    __shared__ __align__(16) float tile[2 * 32 * 128];
+    const int kvh = blockIdx.y, hg = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x * 8 + warp;
+    const bool live = t < T;
+    const int last_pos = pos0 + min(T, blockIdx.x * 8 + 8) - 1; // last position any token of the block sees
+    const int my_pos = pos0 + t;
+    const int h0 = kvh * KV_MUL + hg * HW;
+    float4 qv[HW];
+#pragma unroll
+    for (int j = 0; j < HW; ++j)
+        qv[j] = live ? *reinterpret_cast<const float4*>(q + ((size_t) t * Hl + h0 + j) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    AttnState<HW> st;
+    attn_state_reset(st);
+    const float* K = k_layer + (size_t) kvh * S * 128;
+    const float* V = v_layer + (size_t) kvh * S * 128;
+    for (int p0 = 0; p0 <= last_pos; p0 += 32) {
+        const int rows = min(32, last_pos + 1 - p0);
+        __syncthreads();
+        for (int i = tid; i < rows * 32; i += 256) {
+            reinterpret_cast<float4*>(tile)[i] = *reinterpret_cast<const float4*>(K + (size_t) p0 * 128 + (size_t) i * 4);
+            reinterpret_cast<float4*>(tile + 32 * 128)[i] = *reinterpret_cast<const float4*>(V + (size_t) p0 * 128 + (size_t) i * 4);
+        }
+        __syncthreads();
+        const int cnt = live ? min(rows, my_pos + 1 - p0) : 0;
+        if (cnt > 0) attn_rows<HW>(tile, cnt, tile, cnt, 32 * 128, qv, st, lane);
+    }
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < HW; ++j) {
+            float4 o;
+            o.x = __fdiv_rn(st.acc[j].x, st.l[j]);
+            o.y = __fdiv_rn(st.acc[j].y, st.l[j]);
+            o.z = __fdiv_rn(st.acc[j].z, st.l[j]);
+            o.w = __fdiv_rn(st.acc[j].w, st.l[j]);
+            *reinterpret_cast<float4*>(out + ((size_t) t * Hl + h0 + j) * 128 + lane * 4) = o;
+        }
+    }
+}
+
+// residual add over a chunk (forward.c:295-298, 335-338)
+__global__ void k_add_rows(float* __restrict__ x, const float* __restrict__ y, size_t n) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = __fadd_rn(x[i], y[i]);
+}
+
+int ensure_bufs(QwenCudaCtx* c, PrefillBufs*& pb, int T) {
+    if (!pb) pb = new PrefillBufs();
+    if (pb->cap >= T) return 0;
+    const int cap = (T + 127) / 128 * 128;
+    const size_t maxn = (size_t) std::max(c->D, std::max(c->Pl, c->Hdl));
+    void* old[] = {pb->tokens, pb->x, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
+    for (void* o : old)
+        if (o) cudaFree(o);
+    *pb = PrefillBufs();
+    QW_CUDA(cudaMalloc((void**) &pb->tokens, (size_t) cap * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->x, (size_t) cap * c->D * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->xb, (size_t) cap * c->D * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->qkv, (size_t) cap * (c->Pl + 2 * c->Kl) * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->q, (size_t) cap * c->Pl * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->att, (size_t) cap * c->Pl * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->h13, (size_t) cap * 2 * c->Hdl * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->q8, (size_t) cap * maxn));
+    QW_CUDA(cudaMalloc((void**) &pb->xsT, (size_t) (maxn / 64) * cap * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->err, 4));
+    QW_CUDA(cudaMemset(pb->err, 0, 4));
+    pb->cap = cap;
+    return 0;
+}
+
+} // namespace
+
+static PrefillBufs*& bufs_of(QwenCudaCtx* c) { return *reinterpret_cast<PrefillBufs**>(&c->prefill); }
+
+void qw_prefill_free(QwenCudaCtx* c) {
+    PrefillBufs* pb = bufs_of(c);
+    if (!pb) return;
+    void* old[] = {pb->tokens, pb->x, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
+    for (void* o : old)
+        if (o) cudaFree(o);
+    delete pb;
+    c->prefill = nullptr;
+}
+
+// one chunk of T tokens at positions pos0 .. pos0 + T - 1; leaves the chunk's final residual rows in pb->x
+static int prefill_chunk(QwenCudaCtx* c, PrefillBufs* pb, const int* tokens_host, int T, int pos0) {
+    cudaStream_t st = c->stream;
+    const int D = c->D, Pl = c->Pl, Kl = c->Kl, Hdl = c->Hdl, Tpad = pb->cap;
+    const int kv_mul = c->Hl / c->KVHl;
+    QW_CUDA(cudaMemcpyAsync(pb->tokens, tokens_host, (size_t) T * 4, cudaMemcpyHostToDevice, st));
+    k_embed_rows<<<T, 256, 0, st>>>(pb->x, c->w_emb, pb->tokens, D);
+    auto gemm = [&](const uint8_t* w, float* out, int d, int n) {
+        return qw_prefill_gemm(w, pb->q8, pb->xsT, out, nullptr, d, n, T, Tpad, pb->err, st, nullptr);
+    };
+    const size_t TD = (size_t) T * D;
+    for (int l = 0; l < c->L; ++l) {
+        const size_t loff = (size_t) l * c->KVHl * c->S * 128;
+        // attention block (forward.c:254-298)
+        k_prep_quant<<<T, 256, 0, st>>>(pb->x, c->att_norm + (size_t) l * D, pb->q8, pb->xsT, D, Tpad, 0);
+        if (gemm(c->w_qkv + l * c->w_qkv_stride, pb->qkv, Pl + 2 * Kl, D)) return -1;
+        k_qkv_post_rows<<<dim3(T, c->Hl + 2 * c->KVHl), 128, 0, st>>>(pb->qkv, pb->q, c->k_cache + loff, c->v_cache + loff,
+                                                                     c->q_norm + (size_t) l * 128, c->k_norm + (size_t) l * 128,
+                                                                     c->rope_cos, c->rope_sin, c->Hl, c->KVHl, c->S, pos0);
+        const dim3 ag((T + 7) / 8, c->KVHl, kv_mul > 4 ? kv_mul / 4 : 1);
+        switch (kv_mul) {
+            case 1: k_attn_prefill<1><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            case 2: k_attn_prefill<2><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            case 4: k_attn_prefill<4><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            case 8: k_attn_prefill<8><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            default: qw_set_error("prefill: unsupported GQA ratio %d", kv_mul); return -2;
+        }
+        k_prep_quant<<<T, 256, 0, st>>>(pb->att, nullptr, pb->q8, pb->xsT, Pl, Tpad, 0);
+        if (gemm(c->w_o + l * c->w_o_stride, pb->xb, D, Pl)) return -1;
+        if (qw_tp_allreduce(c, pb->xb, TD)) return -1; // wo is row-parallel under tensor parallelism
+        k_add_rows<<<(unsigned) ((TD + 255) / 256), 256, 0, st>>>(pb->x, pb->xb, TD);
+        // feed-forward block (forward.c:303-338)
+        k_prep_quant<<<T, 256, 0, st>>>(pb->x, c->ffn_norm + (size_t) l * D, pb->q8, pb->xsT, D, Tpad, 0);
+        if (gemm(c->w_13 + l * c->w_13_stride, pb->h13, 2 * Hdl, D)) return -1;
+        k_prep_quant<<<T, 256, 0, st>>>(pb->h13, nullptr, pb->q8, pb->xsT, Hdl, Tpad, 1);
+        if (gemm(c->w_2 + l * c->w_2_stride, pb->xb, D, Hdl)) return -1;
+        if (qw_tp_allreduce(c, pb->xb, TD)) return -1;
+        k_add_rows<<<(unsigned) ((TD + 255) / 256), 256, 0, st>>>(pb->x, pb->xb, TD);
+    }
+    QW_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Prefill n tokens at positions pos0 .. pos0 + n - 1 (KV cache rows written for all of them) and leave the
+// logits of the LAST token in c->logits (c->logits_all under tensor parallelism), as n forward() calls would.
+int qw_prefill(QwenCudaCtx* c, const int* tokens_host, int n, int pos0) {
+    if (n <= 0 || pos0 < 0 || pos0 + n > c->S) {
+        qw_set_error("prefill: positions %d .. %d outside [0, %d)", pos0, pos0 + n - 1, c->S);
+        return -2;
+    }
+    for (int i = 0; i < n; ++i)
+        if (tokens_host[i] < 0 || tokens_host[i] >= c->V) {
+            qw_set_error("prefill: token %d outside [0, %d)", tokens_host[i], c->V);
+            return -2;
+        }
+    if (c->D % 64 || c->Pl % 64 || c->Hdl % 64) {
+        qw_set_error("prefill: dimensions must be multiples of the Q8_0 group");
+        return -2;
+    }
+    PrefillBufs*& pb = bufs_of(c);
+    if (ensure_bufs(c, pb, std::min(n, kChunkTokens))) return -1;
+    int T = 0;
+    for (int t0 = 0; t0 < n; t0 += T) {
+        T = std::min(kChunkTokens, n - t0);
+        if (int rc = prefill_chunk(c, pb, tokens_host + t0, T, pos0 + t0)) return rc;
+    }
+    // final norm + classifier for the last token only (forward.c:344-348)
+    cudaStream_t st = c->stream;
+    const int D = c->D, pad = qw_pad_cols(D);
+    QW_CUDA(cudaMemcpyAsync(c->x, pb->x + (size_t) (T - 1) * D, (size_t) D * 4, cudaMemcpyDeviceToDevice, st));
+    launch_rmsnorm(c->x, c->x, c->out_norm, D, st);
+    if (pad != D) {
+        cudaMemsetAsync(c->aq + D, 0, pad - D, st);
+        cudaMemsetAsync(c->as + D / 64, 0, (size_t) (pad - D) / 64 * 4, st);
+    }
+    launch_quantize(c->x, c->aq, c->as, D, st);
+    launch_gemv_sg(c->w_cls, c->aq, c->as, c->logits, c->Vl, D, nullptr, st);
+    if (c->tp_size > 1 && qw_tp_allgather(c, c->logits, c->logits_all, c->Vl)) return -1;
+    QW_CUDA(cudaGetLastError());
+    int herr = 0;
+    QW_CUDA(cudaMemcpyAsync(&herr, pb->err, 4, cudaMemcpyDeviceToHost, st));
+    QW_CUDA(cudaStreamSynchronize(st));
+    if (herr) {
+        qw_set_error("prefill: GEMM pipeline wait %d timed out", herr);
+        cudaMemsetAsync(pb->err, 0, 4, st);
+        return -3;
+    }
+    return 0;
+}
