@@ -124,6 +124,9 @@ int qwen_cuda_kv_read(QwenCudaCtx* ctx, int layer, int pos0, int npos, float* k_
 /* Read back a device activation by name ("x", "q", "att", "h", "aq", "as") for layer-by-layer
  * parity tests. Returns the number of elements copied or a negative code. */
 int qwen_cuda_debug_read(QwenCudaCtx* ctx, const char* what, void* host, size_t max_bytes);
+/* Test hook: the quantiser fused into the persistent kernel's prologues (reciprocal candidate + exact
+ * fallback), host in / host out; must equal q8_quantize bit for bit. n % 64 == 0. */
+int qwen_cuda_debug_quantize_fused(int8_t* q, float* s, const float* x, int n);
 /* Debug: run only the first n layers of the step (then final norm + classifier); -1 = all. */
 int qwen_cuda_debug_set_layers(QwenCudaCtx* ctx, int n);
 /* Debug: per-CTA phase timestamps (globaltimer ns) of the persistent kernel, [grid][L+1][16].

@@ -106,6 +106,7 @@ class QwenLib:
         L.qwen_cuda_kv_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_kv_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_debug_set_layers.argtypes = [C.c_void_p, C.c_int]
+        L.qwen_cuda_debug_quantize_fused.argtypes = [c_int8_p, c_float_p, c_float_p, C.c_int]
         L.qwen_cuda_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
         L.qwen_cuda_matmul_group_dots.argtypes = [c_int32_p, c_int8_p, c_int8_p, C.c_int, C.c_int, C.c_int]
         L.qwen_cuda_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p]
@@ -163,6 +164,14 @@ class QwenLib:
                                                  _i8(np.ascontiguousarray(xq)), _fp(np.ascontiguousarray(xs)), _i8(wq), _fp(ws),
                                                  n, d, T, reps, C.byref(ms)), "matmul_batch")
         return out, dots, ms.value
+
+    def quantize_fused(self, x):
+        """The persistent decode kernel's fused quantiser on a host vector (test hook)."""
+        x = np.ascontiguousarray(x, np.float32)
+        q = np.zeros(x.size, np.int8)
+        s = np.zeros(x.size // 64, np.float32)
+        self._ok(self.lib.qwen_cuda_debug_quantize_fused(_i8(q), _fp(s), _fp(x), x.size), "quantize_fused")
+        return q, s
 
     def rmsnorm(self, x, w):
         x = np.ascontiguousarray(x, np.float32)

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 
+#include <vector>
+
 #include "common.cuh"
 
 int qw_attention_device(QwenCudaCtx* c, int layer, int pos, const float* q_dev, float* out_dev);
@@ -247,6 +249,34 @@ extern "C" int qwen_cuda_debug_tile_log(QwenCudaCtx* c, int warp, unsigned long 
 extern "C" int qwen_cuda_debug_profile_enable(QwenCudaCtx* c) { return c ? qw_mega_profile_enable(c) : -2; }
 extern "C" int qwen_cuda_debug_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
     return c ? qw_mega_profile_read(c, host, max_elems) : -2;
+}
+
+void qw_mega_quant_records(const float* x, int n, uint8_t* sg, cudaStream_t st);
+// Test hook: the quantiser fused into the persistent decode kernel's prologues (reciprocal candidate with an
+// exact-division fallback) applied to a host vector; must equal q8_quantize (reference q8.c:5-30) bit for bit.
+extern "C" int qwen_cuda_debug_quantize_fused(int8_t* q, float* s, const float* x, int n) {
+    if (!q || !s || !x || n <= 0 || n % 64) return -2;
+    const int recs = qw_sg_per_row(n);
+    float* dx = nullptr;
+    uint8_t* dsg = nullptr;
+    std::vector<uint8_t> h((size_t) recs * QW_SG_BYTES);
+    int rc = -1;
+    do {
+        if (cudaMalloc((void**) &dx, (size_t) n * 4) || cudaMalloc((void**) &dsg, h.size())) break;
+        if (cudaMemcpy(dx, x, (size_t) n * 4, cudaMemcpyHostToDevice)) break;
+        qw_mega_quant_records(dx, n, dsg, 0);
+        if (cudaMemcpy(h.data(), dsg, h.size(), cudaMemcpyDeviceToHost)) break;
+        for (int g = 0; g < n / 64; ++g) {
+            const uint8_t* rec = h.data() + (size_t) (g >> 2) * QW_SG_BYTES;
+            memcpy(q + (size_t) g * 64, rec + (g & 3) * 64, 64);
+            memcpy(s + g, rec + 256 + (g & 3) * 4, 4);
+        }
+        rc = 0;
+    } while (0);
+    if (rc) qw_set_error("debug_quantize_fused: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(dx);
+    cudaFree(dsg);
+    return rc;
 }
 
 extern "C" int qwen_cuda_debug_set_layers(QwenCudaCtx* c, int n) {

@@ -994,6 +994,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ 
     consumer<KV_MUL>(sh, p);
 }
 
+// test hook: the decode kernel's own quantiser (quant_record: reciprocal candidate + exact fallback) over a
+// plain vector, one warp per 256-column record, output in SG layout
+__global__ void k_quant_records(const float* __restrict__ x, int n, uint8_t* __restrict__ sg) {
+    const int lane = threadIdx.x & 31, rec = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (rec >= qw_sg_per_row(n)) return;
+    const bool live = rec * 4 + (lane >> 3) < n / 64;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = live ? x[rec * 256 + lane * 8 + i] : 0.0f;
+    quant_record(sg, rec, lane, v, live);
+}
+
 __global__ void k_fill_u32(uint32_t* dst, size_t n, uint32_t v) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) dst[i] = v;
 }
@@ -1167,6 +1179,12 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
 }
 
 int qw_decode_mega_launches(const QwenCudaCtx*) { return 1; }
+
+// test hook behind qwen_cuda_debug_quantize_fused: x[n] (device) -> SG-layout codes + scales (device)
+void qw_mega_quant_records(const float* x, int n, uint8_t* sg, cudaStream_t st) {
+    const int recs = qw_sg_per_row(n);
+    k_quant_records<<<(recs + 7) / 8, 256, 0, st>>>(x, n, sg);
+}
 
 // debug: where the last persistent-kernel step left the vector `what` of the last layer it ran
 const float* qw_mega_debug_ptr(QwenCudaCtx* c, const char* what) {

@@ -77,7 +77,11 @@ __global__ void __launch_bounds__(512, 1) k_fanin(uint32_t* arena, int D, int ho
                 const int row = r0 + 2 * u + lane;
                 if (lane < 2 && row < r1) store_u32<ST>(vec + row, __float_as_uint(acc + (float) row));
             }
-            if (FENCE) __threadfence();
+            if (FENCE == 1) __threadfence();
+            if (FENCE == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            if (FENCE == 3) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(arena + (size_t) hops * D + 32 * (b * 16 + warp)), "r"(0u) : "memory");
+            if (FENCE == 4) asm volatile("membar.gl;" ::: "memory");
+            if (FENCE == 5) asm volatile("fence.proxy.alias;" ::: "memory");
             // consume: poll the whole vector, lane owns 8 consecutive values of record warp, warp + 15
             for (int rec = warp; rec * 256 < D; rec += 15) {
                 const uint32_t* q = vec + rec * 256 + lane * 8;
@@ -293,29 +297,11 @@ int main() {
     }
     for (int D : {2560, 9728}) {
         run_fan<0, 0, 0>("st.relaxed.gpu, spin", buf, out, sink, D);
-        run_fan<0, 0, 1>("st.relaxed.gpu + fence, spin", buf, out, sink, D);
-        run_fan<0, 100, 0>("st.relaxed.gpu, nanosleep 100", buf, out, sink, D);
-        run_fan<0, 400, 0>("st.relaxed.gpu, nanosleep 400", buf, out, sink, D);
-        run_fan<1, 0, 0>("st.volatile, spin", buf, out, sink, D);
-        run_fan<3, 0, 0>("atomicExch, spin", buf, out, sink, D);
-        run_fan<7, 0, 0>("red.add, spin", buf, out, sink, D);
-        run_fan<7, 100, 0>("red.add, nanosleep 100", buf, out, sink, D);
-        run_fan<5, 0, 0>("st.cg, spin", buf, out, sink, D);
-        {
-            const int hops = 64, G = 148;
-            for (int rep = 0; rep < 2; ++rep) {
-                cudaMemset(ctr, 0, 8);
-                void* args[] = {&buf, &ctr, (void*) &D, (void*) &hops, &out, &sink};
-                cudaLaunchCooperativeKernel((const void*) k_barrier, dim3(G), dim3(512), args, 0, 0);
-                cudaError_t e = cudaDeviceSynchronize();
-                if (e) printf("barrier: %s\n", cudaGetErrorString(e));
-            }
-            unsigned long long t[148];
-            cudaMemcpy(t, out, sizeof t, cudaMemcpyDeviceToHost);
-            unsigned long long mx = 0;
-            for (int i = 0; i < G; ++i) mx = t[i] > mx ? t[i] : mx;
-            printf("fanin D=%5d %-40s %6.2f us per hop\n", D, "counter barrier + load (old way)", (double) mx / hops / 1e3);
-        }
+        run_fan<0, 0, 1>("st.relaxed.gpu + __threadfence", buf, out, sink, D);
+        run_fan<0, 0, 2>("st.relaxed.gpu + fence.acq_rel.gpu", buf, out, sink, D);
+        run_fan<0, 0, 3>("st.relaxed.gpu + red.release.gpu dummy", buf, out, sink, D);
+        run_fan<0, 0, 4>("st.relaxed.gpu + membar.gl", buf, out, sink, D);
+        run_fan<4, 0, 0>("st.release.gpu each store", buf, out, sink, D);
     }
     {
         uint8_t* big;

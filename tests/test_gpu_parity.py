@@ -375,6 +375,21 @@ def test_quantize_fast_path_bit_exact_on_many_values(qlib, oracle):
     oq, os_ = oracle.q8_quantize(x)
     same(s, os_)
     same(q, oq)
+    # the quantiser fused into the persistent decode kernel (x * rcp(scale) candidate, exact division within 1e-3
+    # of a rounding boundary) on the same adversarial values, plus denormal / huge / zero groups
+    q, s = qlib.quantize_fused(x)
+    same(s, os_)
+    same(q, oq)
+    edge = np.zeros(64 * 6, np.float32)
+    edge[64:128] = np.float32(1e-41) * rng.standard_normal(64).astype(np.float32)        # denormal group: scale underflows
+    edge[128:192] = np.float32(3e38) * rng.uniform(-1, 1, 64).astype(np.float32)          # near FLT_MAX
+    edge[192:256] = np.float32(1.17549435e-38) * rng.uniform(-4, 4, 64).astype(np.float32)
+    edge[256:320] = np.arange(64, dtype=np.float32) - 31.5                               # exact halves after scaling
+    edge[320:384] = rng.standard_normal(64).astype(np.float32)
+    q, s = qlib.quantize_fused(edge)
+    oq, os_ = oracle.q8_quantize(edge)
+    same(s, os_)
+    same(q, oq)
 
 
 @pytest.mark.parametrize("n,d,T", [(64, 8, 1), (320, 300, 200), (2560, 384, 256), (1024, 128, 130)])
