@@ -85,6 +85,10 @@ SHAPES = {
     "tiny-untied": Shape("tiny-untied", 256, 512, 3, 8, 2, 384, seq_len=192, shared_classifier=0),
     "small": Shape("small", 512, 1536, 4, 8, 4, 2048, seq_len=1024),
     "0.6b-l1": Shape("0.6b-l1", 1024, 3072, 1, 16, 8, 4096, seq_len=256),
+    # two layers of the real 4B / 8B / 32B layer shapes (GQA 4, 4, 8; hidden 9728 / 12288 / 25600) with a small vocabulary
+    "4b-l2": Shape("4b-l2", 2560, 9728, 2, 32, 8, 4096, seq_len=4096),
+    "8b-l2": Shape("8b-l2", 4096, 12288, 2, 32, 8, 4096, seq_len=4096, shared_classifier=0),
+    "32b-l2": Shape("32b-l2", 5120, 25600, 2, 64, 8, 4096, seq_len=4096, shared_classifier=0),
     "0.6b": Shape("0.6b", 1024, 3072, 28, 16, 8, 151936),
     "1.7b": Shape("1.7b", 2048, 6144, 28, 16, 8, 151936),
     "4b": Shape("4b", 2560, 9728, 36, 32, 8, 151936),
