@@ -15,13 +15,17 @@
 //             (cp.async.bulk.tensor.2d, SWIZZLE_64B), the matching 128-token x 64-byte box of the
 //             int8 activations, and the 128 activation scales of the group (bulk copy).
 //   warp 1  : MMA issuer (one elected lane): 2 x tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128,
-//             K=32) per group into one of two TMEM accumulator buffers, tcgen05.commit to mbarriers.
-//   warps 2-9: epilogue. tcgen05.ld the group's 128x128 int32 tile (warp w reads TMEM lanes
-//             32*(w%4).., columns 64*(w/4)..), scale-promote to fp32 in registers, release the TMEM
+//             K=32) per group into one of four TMEM accumulator buffers, tcgen05.commit to mbarriers.
+//   warps 2-17: epilogue. tcgen05.ld the group's 128x128 int32 tile (warp w reads TMEM lanes
+//             32*(w%4).., 32 columns), scale-promote to fp32 in registers, release the TMEM
 //             buffer; after the last group store out[t][i].
 // Because the scales change every 64 k-elements on both operands the accumulator must leave TMEM
-// every 2 MMAs: the CUDA-core promotion (4 ops per MAC-column), not the tensor pipe, is the ceiling
-// (SURVEY.md H4). Block-scaled MMA kinds do not apply (UE8M0 / E4M3 scale formats only).
+// every 2 MMAs: the CUDA-core promotion (3 instructions per output per group), not the tensor pipe, is the
+// ceiling. Block-scaled MMA kinds do not apply (UE8M0 / E4M3 scale formats only).
+// Measured on B200 (4B w1/w3, T = 512): 153 us with 8 epilogue warps, 132 us with 16; of those ~45 us are the
+// promotion arithmetic (skipping it: 96 us) and the MMAs themselves are free (not issuing them: -7 %). Deeper
+// TMEM / shared-memory pipelines (2 -> 4 accumulators, 6 -> 12 stages), 128-byte SWIZZLE_128B operand rows
+// (two groups per stage) and prefetching the weight scales changed nothing or lost a few per cent.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -31,10 +35,11 @@ namespace {
 
 constexpr int kTileM = 128;   // weight rows per tile  (UMMA M, TMEM lanes)
 constexpr int kTileN = 128;   // tokens per tile       (UMMA N, TMEM columns)
-constexpr int kStages = 6;
+constexpr int kStages = 12;
+constexpr int kAccBufs = 4;   // TMEM accumulator buffers: 4 x 128 columns = all of TMEM
 constexpr int kABytes = kTileM * 64, kBBytes = kTileN * 64, kSBytes = kTileN * 4;
 constexpr int kStageBytes = kABytes + kBBytes + 1024; // scales padded to keep stages 1024-aligned
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;  // 4 per scheduler: one warp's TMEM load / barrier wait hides behind the others' arithmetic
 constexpr int kThreadsG = 32 * (2 + kEpiWarps);
 constexpr unsigned long long kTimeoutNsG = 2000000000ull;
 
@@ -127,6 +132,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
         : "memory");
 }
 
+// Packed fp32x2 multiplies for the promotion epilogue (sm_100 FMUL2: two IEEE fp32 products per instruction).
+// CAREFUL: ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 -- and even fma(x, y, -0) + fma(t, 1, acc) --
+// into ONE FFMA2, which rounds once where the reference rounds twice (forward.c:94-96), -fmad=false or not.
+// So only the two multiplies are packed and the accumulation stays two scalar FADDs: the SASS must show
+// 2 FMUL2 + 2 FADD per pair of tokens (and no FFMA2 / FFMA);
+// tests/test_gpu_parity.py::test_prefill_matmul_batch_bit_identical_to_reference_matmul is the guard.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
 struct GemmParams {
     const uint8_t* w;      // SG layout, rows x n
     const float* xsT;      // [groups][Tpad] activation scales, transposed
@@ -141,28 +166,28 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_64B operands want their 512-byte atoms aligned; do not rely on where static shared ends
     uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t bars[2 * kStages + 4];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 2 * kAccBufs];
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kTileM, t0 = blockIdx.y * kTileN;
     const int groups = p.n / 64;
     const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kStages]);
-    const uint32_t tfull0 = s_u32(&bars[2 * kStages]), tempty0 = s_u32(&bars[2 * kStages + 2]);
+    const uint32_t tfull0 = s_u32(&bars[2 * kStages]), tempty0 = s_u32(&bars[2 * kStages + kAccBufs]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mb_init(full0 + 8 * s, 1);
             mb_init(empty0 + 8 * s, 1 + kEpiWarps); // MMA retire + every epilogue warp done with the stage's scales
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kAccBufs; ++b) {
             mb_init(tfull0 + 8 * b, 1);
             mb_init(tempty0 + 8 * b, kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) { // TMEM: 2 accumulator buffers x 128 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(256)
+    if (warp == 1) { // TMEM: kAccBufs accumulator buffers x 128 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(kAccBufs * kTileN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -190,8 +215,8 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_i8(kTileM, kTileN);
             for (int g = 0; g < groups; ++g) {
-                const int s = g % kStages, b = g & 1;
-                if (!mb_wait(tempty0 + 8 * b, ((g >> 1) & 1) ^ 1, p.err, 2)) break; // epilogue drained this buffer
+                const int s = g % kStages, b = g % kAccBufs;
+                if (!mb_wait(tempty0 + 8 * b, ((g / kAccBufs) & 1) ^ 1, p.err, 2)) break; // epilogue drained this buffer
                 if (!mb_wait(full0 + 8 * s, (g / kStages) & 1, p.err, 3)) break;    // operands landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = s_u32(smem + (size_t) s * kStageBytes);
@@ -206,49 +231,54 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     } else {
         // ------------------------------------------------------------ epilogue: scale-promote per group
         const int ew = warp - 2;
-        // a warp may only touch TMEM lanes 32*(warp_id % 4) .. +31 (hardware rule, CTA warp id): warps 2..5
-        // take columns 0..63, warps 6..9 columns 64..127, and inside each set warp%4 picks the lane quarter
+        // a warp may only touch TMEM lanes 32*(warp_id % 4) .. +31 (hardware rule, CTA warp id): warp%4 picks the
+        // lane quarter (32 weight rows), (warp - 2) / 4 the 32-token column block
         const int lane_blk = warp & 3, col_blk = ew >> 2;
         const int i = row0 + lane_blk * 32 + lane;          // weight row of this thread
         const bool row_ok = i < p.d;
         const uint8_t* wrow = p.w + (size_t) (row_ok ? i : 0) * qw_row_bytes(p.n);
-        float acc[64];
+        float acc[32];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
+        for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
         bool ok = true;
         for (int g = 0; g < groups && ok; ++g) {
-            const int s = g % kStages, b = g & 1;
+            const int s = g % kStages, b = g % kAccBufs;
             const float wsc = row_ok ? __ldg(reinterpret_cast<const float*>(wrow + (g >> 2) * QW_SG_BYTES + 256 + (g & 3) * 4)) : 0.0f;
-            ok = mb_wait(tfull0 + 8 * b, (g >> 1) & 1, p.err, 4);
+            ok = mb_wait(tfull0 + 8 * b, (g / kAccBufs) & 1, p.err, 4);
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float* xs = reinterpret_cast<const float*>(smem + (size_t) s * kStageBytes + kABytes + kBBytes) + col_blk * 64;
-            const uint32_t taddr = tmem_base + ((uint32_t) (lane_blk * 32) << 16) + b * kTileN + col_blk * 64;
-            int v0[32], v1[32];
+            const float* xs = reinterpret_cast<const float*>(smem + (size_t) s * kStageBytes + kABytes + kBBytes) + col_blk * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t) (lane_blk * 32) << 16) + b * kTileN + col_blk * 32;
+            int v0[32];
             tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mb_arrive(tempty0 + 8 * b); // accumulator buffer may be overwritten
             if (p.dots && row_ok) {
 #pragma unroll
-                for (int c = 0; c < 64; ++c) {
-                    const int t = t0 + col_blk * 64 + c;
-                    if (t < p.T) p.dots[((size_t) t * p.d + i) * groups + g] = c < 32 ? v0[c] : v1[c - 32];
+                for (int c = 0; c < 32; ++c) {
+                    const int t = t0 + col_blk * 32 + c;
+                    if (t < p.T) p.dots[((size_t) t * p.d + i) * groups + g] = v0[c];
                 }
             }
+            // acc += ((float) dot * ws) * xs, the reference's two roundings and one add (forward.c:94-96)
+            const unsigned long long ws2 = pack2(wsc, wsc);
+            const unsigned long long* xs2 = reinterpret_cast<const unsigned long long*>(xs);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc[c] = __fadd_rn(acc[c], q8_term(v0[c], wsc, xs[c]));
-#pragma unroll
-            for (int c = 0; c < 32; ++c) acc[32 + c] = __fadd_rn(acc[32 + c], q8_term(v1[c], wsc, xs[32 + c]));
+            for (int c = 0; c < 16; ++c) {
+                float lo, hi; // the two multiplies packed (FMUL2), the add scalar: ptxas cannot contract across the two forms
+                unpack2(mul2(mul2(pack2((float) v0[2 * c], (float) v0[2 * c + 1]), ws2), xs2[c]), lo, hi);
+                acc[2 * c] = __fadd_rn(acc[2 * c], lo);
+                acc[2 * c + 1] = __fadd_rn(acc[2 * c + 1], hi);
+            }
             __syncwarp();
             if (lane == 0) mb_arrive(empty0 + 8 * s); // done with this stage's activation scales
         }
         if (ok && row_ok) {
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                const int t = t0 + col_blk * 64 + c;
+            for (int c = 0; c < 32; ++c) {
+                const int t = t0 + col_blk * 32 + c;
                 if (t < p.T) p.out[(size_t) t * p.d + i] = acc[c];
             }
         }
@@ -256,7 +286,7 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kAccBufs * kTileN) : "memory");
     }
 }
 
