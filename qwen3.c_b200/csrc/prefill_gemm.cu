@@ -34,13 +34,13 @@
 namespace {
 
 constexpr int kTileM = 128;   // weight rows per tile  (UMMA M, TMEM lanes)
-constexpr int kTileN = 128;   // tokens per tile       (UMMA N, TMEM columns)
+constexpr int kTileN = 128;   // tokens per tile       (UMMA N, TMEM columns); 64 for grids that would leave SMs idle
 constexpr int kStages = 12;
 constexpr int kAccBufs = 4;   // TMEM accumulator buffers: 4 x 128 columns = all of TMEM
-constexpr int kABytes = kTileM * 64, kBBytes = kTileN * 64, kSBytes = kTileN * 4;
-constexpr int kStageBytes = kABytes + kBBytes + 1024; // scales padded to keep stages 1024-aligned
-constexpr int kEpiWarps = 16;  // 4 per scheduler: one warp's TMEM load / barrier wait hides behind the others' arithmetic
-constexpr int kThreadsG = 32 * (2 + kEpiWarps);
+constexpr int kABytes = kTileM * 64;
+constexpr int kStageBytes = kABytes + kTileN * 64 + 1024; // A, B (sized for the wide tile), scales; stages stay 1024-aligned
+constexpr int kMaxEpiWarps = 16; // wide tile: 4 per scheduler, one warp's TMEM load / barrier wait hides behind the others' arithmetic
+constexpr int kThreadsG = 32 * (2 + kMaxEpiWarps);
 constexpr unsigned long long kTimeoutNsG = 2000000000ull;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -161,6 +161,8 @@ struct GemmParams {
     int* err;
 };
 
+// TN = tokens per tile (128, or 64 when 128-token tiles would not fill the SMs); 4 * TN / 32 epilogue warps
+template <int TN>
 __global__ void __launch_bounds__(kThreadsG, 1)
 k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -169,7 +171,8 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     __shared__ __align__(8) uint64_t bars[2 * kStages + 2 * kAccBufs];
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * kTileM, t0 = blockIdx.y * kTileN;
+    constexpr int kEpiWarps = 4 * TN / 32, kBBytes = TN * 64, kSBytes = TN * 4;
+    const int row0 = blockIdx.x * kTileM, t0 = blockIdx.y * TN;
     const int groups = p.n / 64;
     const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kStages]);
     const uint32_t tfull0 = s_u32(&bars[2 * kStages]), tempty0 = s_u32(&bars[2 * kStages + kAccBufs]);
@@ -187,7 +190,7 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) { // TMEM: kAccBufs accumulator buffers x 128 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(kAccBufs * kTileN)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(kAccBufs * TN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -207,20 +210,20 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 mb_expect(full0 + 8 * s, kABytes + kBBytes + kSBytes);
                 tma_2d(base, &map_w, (g >> 2) * QW_SG_BYTES + (g & 3) * 64, row0, full0 + 8 * s);
                 tma_2d(base + kABytes, &map_x, g * 64, t0, full0 + 8 * s);
-                bulk_1d(base + kABytes + kBBytes, p.xsT + (size_t) g * p.Tpad + t0, kSBytes, full0 + 8 * s);
+                bulk_1d(base + kABytes + kTileN * 64, p.xsT + (size_t) g * p.Tpad + t0, kSBytes, full0 + 8 * s);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_i8(kTileM, kTileN);
+            const uint32_t idesc = umma_idesc_i8(kTileM, TN);
             for (int g = 0; g < groups; ++g) {
                 const int s = g % kStages, b = g % kAccBufs;
                 if (!mb_wait(tempty0 + 8 * b, ((g / kAccBufs) & 1) ^ 1, p.err, 2)) break; // epilogue drained this buffer
                 if (!mb_wait(full0 + 8 * s, (g / kStages) & 1, p.err, 3)) break;    // operands landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = s_u32(smem + (size_t) s * kStageBytes);
-                const uint32_t d = tmem_base + b * kTileN;
+                const uint32_t d = tmem_base + b * TN;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) // 64 codes = 2 x K32; the k-th 32-byte slice of every swizzled row
                     umma_i8(d, umma_desc_sw64(base + 32 * k), umma_desc_sw64(base + kABytes + 32 * k), idesc, k);
@@ -231,6 +234,7 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     } else {
         // ------------------------------------------------------------ epilogue: scale-promote per group
         const int ew = warp - 2;
+        if (ew < kEpiWarps) {
         // a warp may only touch TMEM lanes 32*(warp_id % 4) .. +31 (hardware rule, CTA warp id): warp%4 picks the
         // lane quarter (32 weight rows), (warp - 2) / 4 the 32-token column block
         const int lane_blk = warp & 3, col_blk = ew >> 2;
@@ -247,8 +251,8 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             ok = mb_wait(tfull0 + 8 * b, (g / kAccBufs) & 1, p.err, 4);
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float* xs = reinterpret_cast<const float*>(smem + (size_t) s * kStageBytes + kABytes + kBBytes) + col_blk * 32;
-            const uint32_t taddr = tmem_base + ((uint32_t) (lane_blk * 32) << 16) + b * kTileN + col_blk * 32;
+            const float* xs = reinterpret_cast<const float*>(smem + (size_t) s * kStageBytes + kABytes + kTileN * 64) + col_blk * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t) (lane_blk * 32) << 16) + b * TN + col_blk * 32;
             int v0[32];
             tmem_ld32(taddr, v0);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -282,11 +286,12 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 if (t < p.T) p.out[(size_t) t * p.d + i] = acc[c];
             }
         }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kAccBufs * kTileN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kAccBufs * TN) : "memory");
     }
 }
 
@@ -337,22 +342,37 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
         return -2;
     }
     CUtensorMap mw, mx;
-    if (make_map(&mw, w, qw_row_bytes(n), (uint64_t) d, kTileM) || make_map(&mx, xq, (uint64_t) n, (uint64_t) T, kTileN)) return -1;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // 128-token tiles unless 64-token tiles finish sooner: time ~ waves x cost of one tile, and a 64-token tile costs
+    // ~0.7 of a 128-token one (measured). E.g. 1.7B wo / w2 at T = 512: 64 wide tiles on 148 SMs vs 128 narrow ones
+    // in one wave -> narrow; 4B w2: 80 wide tiles in one wave vs 160 narrow ones in two -> wide.
+    const int rt = (d + kTileM - 1) / kTileM;
+    const int waves_w = (rt * ((T + kTileN - 1) / kTileN) + sms - 1) / sms, waves_n = (rt * ((T + 63) / 64) + sms - 1) / sms;
+    const bool wide = waves_w * 100 <= waves_n * 72;
+    const int TN = wide ? kTileN : 64;
+    if (make_map(&mw, w, qw_row_bytes(n), (uint64_t) d, kTileM) || make_map(&mx, xq, (uint64_t) n, (uint64_t) T, TN)) return -1;
     static bool attr = false;
     const size_t smem = (size_t) kStages * kStageBytes + 1024;
     if (!attr) {
-        QW_CUDA(cudaFuncSetAttribute(k_prefill_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        QW_CUDA(cudaFuncSetAttribute(k_prefill_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        QW_CUDA(cudaFuncSetAttribute(k_prefill_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr = true;
     }
     GemmParams p{w, xsT, out, dots, d, n, T, Tpad, err_dev};
-    const dim3 grid((d + kTileM - 1) / kTileM, (T + kTileN - 1) / kTileN);
+    const dim3 grid((d + kTileM - 1) / kTileM, (T + TN - 1) / TN);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms_out) {
         QW_CUDA(cudaEventCreate(&e0));
         QW_CUDA(cudaEventCreate(&e1));
         QW_CUDA(cudaEventRecord(e0, st));
     }
-    k_prefill_gemm<<<grid, kThreadsG, smem, st>>>(mw, mx, p);
+    if (wide) k_prefill_gemm<128><<<grid, kThreadsG, smem, st>>>(mw, mx, p);
+    else k_prefill_gemm<64><<<grid, kThreadsG, smem, st>>>(mw, mx, p);
     QW_CUDA(cudaGetLastError());
     if (ms_out) {
         QW_CUDA(cudaEventRecord(e1, st));
