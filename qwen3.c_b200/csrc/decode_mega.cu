@@ -406,6 +406,7 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
         mbar_wait(sh, p, sh.full + slot * 8, par, 3);
         const uint8_t* tile = sh.ring + (size_t) slot * kSlotBytes;
         const int t1 = p.dbg_mode >= 1 ? t0 : min(t0 + upt, total);
+        bool released = false;
         int ufirst = (warp - t0) % kConsumerWarps; // first unit >= t0 owned by this warp (u % 15 == warp)
         if (ufirst < 0) ufirst += kConsumerWarps;
 #pragma unroll 1
@@ -451,6 +452,13 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
                     accb = __fadd_rn(accb, q8_term(db1, *reinterpret_cast<const float*>(rowb + so2), xs1));
                 }
             }
+            if (u + kConsumerWarps >= t1) {
+                // this warp's last unit in the tile: every byte it needs from the ring slot has been consumed by a
+                // dp4a, so the slot goes back to the producer BEFORE the cross-lane reduction and the epilogue
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+                released = true;
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 acca = __fadd_rn(acca, __shfl_xor_sync(0xffffffffu, acca, o));
@@ -463,8 +471,10 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
                 stf_f32(out + grow + lane, KIND == 1 ? __fadd_rn(xres, v) : v);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sh.empty + slot * 8); // this warp is done with the slot
+        if (!released) { // no unit of this warp in the tile
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+        }
     }
     // push this warp's results out NOW: without a fence the stores sit in the SM's write path for
     // microseconds (measured, scripts/ubench/handoff.cu: 2.7 us per hand-off without, 1.05 us with)
