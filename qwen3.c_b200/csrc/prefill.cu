@@ -124,12 +124,18 @@ k_qkv_post_rows(const float* __restrict__ qkv, float* __restrict__ q_out, float*
 // warp w = query token 8 * blockIdx.x + w with the HW query heads of head group blockIdx.z; the 8 tokens
 // share K/V tiles of 32 positions staged in shared memory; each warp runs the decode kernel's online-softmax
 // step (attn_core.cuh) over the positions it may see (0 .. pos0 + t).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+constexpr int kAttnTile = 32;                                   // KV positions per shared-memory tile
+constexpr int kAttnSmem = 2 * 2 * kAttnTile * 128 * 4;          // double-buffered K and V tiles
+
 template <int KV_MUL>
 __global__ void __launch_bounds__(256)
 k_attn_prefill(const float* __restrict__ q, const float* __restrict__ k_layer, const float* __restrict__ v_layer,
                float* __restrict__ out, int Hl, int S, int pos0, int T) {
     constexpr int HW = KV_MUL < 4 ? KV_MUL : 4;
-    __shared__ __align__(16) float tile[2 * 32 * 128];
+    extern __shared__ __align__(16) float tiles[]; // [2 buffers][K 32 x 128 | V 32 x 128]
     const int kvh = blockIdx.y, hg = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x * 8 + warp;
     const bool live = t < T;
@@ -144,16 +150,30 @@ k_attn_prefill(const float* __restrict__ q, const float* __restrict__ k_layer, c
     attn_state_reset(st);
     const float* K = k_layer + (size_t) kvh * S * 128;
     const float* V = v_layer + (size_t) kvh * S * 128;
-    for (int p0 = 0; p0 <= last_pos; p0 += 32) {
-        const int rows = min(32, last_pos + 1 - p0);
-        __syncthreads();
-        for (int i = tid; i < rows * 32; i += 256) {
-            reinterpret_cast<float4*>(tile)[i] = *reinterpret_cast<const float4*>(K + (size_t) p0 * 128 + (size_t) i * 4);
-            reinterpret_cast<float4*>(tile + 32 * 128)[i] = *reinterpret_cast<const float4*>(V + (size_t) p0 * 128 + (size_t) i * 4);
+    // tile `it` (positions 32 it ..) is fetched with cp.async into buffer it & 1 while tile it - 1 is being used
+    auto fetch = [&](int it) {
+        const int p0 = it * kAttnTile;
+        if (p0 <= last_pos) {
+            const int rows = min(kAttnTile, last_pos + 1 - p0);
+            float* kb = tiles + (size_t) (it & 1) * (2 * kAttnTile * 128);
+            for (int i = tid; i < rows * 32; i += 256) {
+                cp_async16(kb + i * 4, K + (size_t) p0 * 128 + (size_t) i * 4);
+                cp_async16(kb + kAttnTile * 128 + i * 4, V + (size_t) p0 * 128 + (size_t) i * 4);
+            }
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0);
+    for (int it = 0; it * kAttnTile <= last_pos; ++it) {
+        fetch(it + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory"); // tile `it` has landed (this thread's part)
+        __syncthreads();                                      // ... and everybody else's
+        const int p0 = it * kAttnTile;
+        const int rows = min(kAttnTile, last_pos + 1 - p0);
         const int cnt = live ? min(rows, my_pos + 1 - p0) : 0;
-        if (cnt > 0) attn_rows<HW>(tile, cnt, tile, cnt, 32 * 128, qv, st, lane);
+        const float* kb = tiles + (size_t) (it & 1) * (2 * kAttnTile * 128);
+        if (cnt > 0) attn_rows<HW>(kb, cnt, kb, cnt, kAttnTile * 128, qv, st, lane);
+        __syncthreads(); // the buffer is refilled by the fetch of the next iteration
     }
     if (live) {
 #pragma unroll
@@ -194,6 +214,10 @@ int ensure_bufs(QwenCudaCtx* c, PrefillBufs*& pb, int T) {
     QW_CUDA(cudaMalloc((void**) &pb->xsT, (size_t) (maxn / 64) * cap * 4));
     QW_CUDA(cudaMalloc((void**) &pb->err, 4));
     QW_CUDA(cudaMemset(pb->err, 0, 4));
+    QW_CUDA(cudaFuncSetAttribute(k_attn_prefill<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    QW_CUDA(cudaFuncSetAttribute(k_attn_prefill<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    QW_CUDA(cudaFuncSetAttribute(k_attn_prefill<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    QW_CUDA(cudaFuncSetAttribute(k_attn_prefill<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     pb->cap = cap;
     return 0;
 }
@@ -233,10 +257,10 @@ static int prefill_chunk(QwenCudaCtx* c, PrefillBufs* pb, const int* tokens_host
                                                                      c->rope_cos, c->rope_sin, c->Hl, c->KVHl, c->S, pos0);
         const dim3 ag((T + 7) / 8, c->KVHl, kv_mul > 4 ? kv_mul / 4 : 1);
         switch (kv_mul) {
-            case 1: k_attn_prefill<1><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
-            case 2: k_attn_prefill<2><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
-            case 4: k_attn_prefill<4><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
-            case 8: k_attn_prefill<8><<<ag, 256, 0, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            case 1: k_attn_prefill<1><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            case 2: k_attn_prefill<2><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            case 4: k_attn_prefill<4><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
+            case 8: k_attn_prefill<8><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
             default: qw_set_error("prefill: unsupported GQA ratio %d", kv_mul); return -2;
         }
         k_prep_quant<<<T, 256, 0, st>>>(pb->att, nullptr, pb->q8, pb->xsT, Pl, Tpad, 0);
