@@ -252,21 +252,28 @@ __device__ __forceinline__ void cta_rows(const MatDesc& m, int perm, int& r0, in
     r1 = (int) (units * (b + 1) / gridDim.x) * m.gran;
 }
 
-// Attention tiles: unit u = (kv head u / nc, chunk u % nc), U = KVH * nc units, block b owns
-// units [U*b/G, U*(b+1)/G).
-__device__ __forceinline__ void attn_units(const MegaParams& p, int& nc, int& u0, int& u1) {
-    nc = p.pos / kChunk + 1;
-    const unsigned U = (unsigned) (p.KVHl * nc); // U * grid < 2^31 (KVH <= 64, S <= 2^17)
-    const unsigned b = (unsigned) my_block(p.perm);
-    u0 = (int) (U * b / gridDim.x);
-    u1 = (int) (U * (b + 1) / gridDim.x);
-}
-// the block whose range contains `unit`
-__device__ __noinline__ int block_of_unit(unsigned unit, unsigned U, unsigned G) {
-    unsigned b = unit * G / U;
-    while (b + 1 < G && U * (b + 1) / G <= unit) ++b;
-    while (b > 0 && U * b / G > unit) --b;
-    return (int) b;
+// Attention work split. Every block serves ONE kv head: kv head h gets the blocks [G*h/KVH, G*(h+1)/KVH) (18 or
+// 19 of 148 for 8 kv heads) and block j of its n attends over the cached positions [pos*j/n, pos*(j+1)/n) -- an
+// even split to the position, streamed as tiles of up to 28 rows that start at the block's own first position.
+// The last block of a kv head also takes this step's own position. (Splitting whole 28-position tiles evenly
+// over all blocks left one block per kv head with two segments -- two query preparations, two merges, two
+// publications -- and 8 vs 9 tiles elsewhere; every combine task waited for the slowest.)
+struct AttnSplit {
+    int kvh, j, n;   // kv head, index of this block among the kv head's n blocks
+    int p_lo, p_hi;  // cached positions [p_lo, p_hi) of this block
+};
+__device__ __forceinline__ AttnSplit attn_split(const MegaParams& p) {
+    const int G = gridDim.x, KVH = p.KVHl, b = my_block(p.perm);
+    int h = b * KVH / G;
+    while ((h + 1) * G / KVH <= b) ++h;
+    const int f0 = h * G / KVH;
+    AttnSplit a;
+    a.kvh = h;
+    a.j = b - f0;
+    a.n = (h + 1) * G / KVH - f0;
+    a.p_lo = (int) ((long long) p.pos * a.j / a.n);
+    a.p_hi = (int) ((long long) p.pos * (a.j + 1) / a.n);
+    return a;
 }
 
 __device__ __forceinline__ void stamp(const MegaParams& p, int l, int k) {
@@ -290,18 +297,11 @@ __device__ __noinline__ void prefetch_subphase(const MegaParams& p, int sp) {
     if (sp > nsp) return;
     const int l = sp / 5, k = sp == nsp ? 5 : sp % 5;
     if (k == 1) {
-        int nc, u0, u1;
-        attn_units(p, nc, u0, u1);
-        for (int u = u0; u < u1;) {
-            const int kvh = u / nc, seg_end = min(u1, (kvh + 1) * nc);
-            const int p0 = (u - kvh * nc) * kChunk;
-            const int cnt = min(p.pos, (seg_end - kvh * nc) * kChunk) - p0;
-            if (cnt > 0) {
-                const size_t off = (((size_t) l * p.KVHl + kvh) * p.S + p0) * 128;
-                prefetch_l2(reinterpret_cast<const uint8_t*>(p.k_cache + off), (size_t) cnt * 512);
-                prefetch_l2(reinterpret_cast<const uint8_t*>(p.v_cache + off), (size_t) cnt * 512);
-            }
-            u = seg_end;
+        const AttnSplit a = attn_split(p);
+        if (a.p_hi > a.p_lo) {
+            const size_t off = (((size_t) l * p.KVHl + a.kvh) * p.S + a.p_lo) * 128;
+            prefetch_l2(reinterpret_cast<const uint8_t*>(p.k_cache + off), (size_t) (a.p_hi - a.p_lo) * 512);
+            prefetch_l2(reinterpret_cast<const uint8_t*>(p.v_cache + off), (size_t) (a.p_hi - a.p_lo) * 512);
         }
     } else {
         const MatDesc& m = p.mat[k == 0 ? 0 : k == 5 ? 4 : k - 1];
@@ -332,25 +332,18 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
         if (k == 1) { // the layer's KV tiles come between QKV and WO
             if (p.l2_ahead) prefetch_subphase(p, sp + 1);
             ++sp;
-            int nc, u0, u1;
-            attn_units(p, nc, u0, u1);
+            const AttnSplit a = attn_split(p);
 #pragma unroll 1
-            for (int u = u0; u < u1; ++u, ++it) {
-                const int kvh = u / nc, c = u % nc;
-                const int p0 = c * kChunk;
-                const int cnt = min(p.pos, p0 + kChunk) - p0; // slot `pos` itself is produced by this step
+            for (int p0 = a.p_lo; p0 < a.p_hi; p0 += kChunk, ++it) {
+                const int cnt = min(kChunk, a.p_hi - p0);
                 const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
                 mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 2);
-                if (cnt > 0) {
-                    const size_t off = (((size_t) l * p.KVHl + kvh) * p.S + p0) * 128;
-                    const uint32_t bytes = (uint32_t) cnt * 512u;
-                    const uint32_t dst = smem_u32(sh.ring + (size_t) slot * kSlotBytes);
-                    mbar_expect_tx(sh.full + slot * 8, 2 * bytes);
-                    bulk_g2s(dst, p.k_cache + off, bytes, sh.full + slot * 8);
-                    bulk_g2s(dst + kChunk * 512, p.v_cache + off, bytes, sh.full + slot * 8);
-                } else {
-                    mbar_arrive(sh.full + slot * 8);
-                }
+                const size_t off = (((size_t) l * p.KVHl + a.kvh) * p.S + p0) * 128;
+                const uint32_t bytes = (uint32_t) cnt * 512u;
+                const uint32_t dst = smem_u32(sh.ring + (size_t) slot * kSlotBytes);
+                mbar_expect_tx(sh.full + slot * 8, 2 * bytes);
+                bulk_g2s(dst, p.k_cache + off, bytes, sh.full + slot * 8);
+                bulk_g2s(dst + kChunk * 512, p.v_cache + off, bytes, sh.full + slot * 8);
             }
         }
         if (p.l2_ahead) prefetch_subphase(p, sp + 1);
@@ -673,9 +666,9 @@ __device__ __forceinline__ void attn_dump(const AttnState<HW>& st, float* slot, 
 // tiles the same memory holds up to 8 dumped warp states for the merge tree.
 constexpr int kScrFloats = 8 * 4 * kPartStride;
 
-// Split-KV attention for the tiles of this CTA. A segment = the CTA's tiles of one KV head; its query
-// heads (and, if the CTA owns the KV head's last chunk, this step's own K/V row: RMSNorm + RoPE,
-// written to the cache for later steps) are prepared once per segment, one warp per head. Warp w
+// Split-KV attention over this CTA's positions of its kv head (attn_split). The query heads (and, on the kv
+// head's last block, this step's own K/V row: RMSNorm + RoPE, written to the cache for later steps) are
+// prepared first, one warp per head. Warp w
 // serves head group w % NHG; the warps of a head group split the segment's cached positions into
 // equal contiguous ranges (a range may straddle two tiles), so the load is balanced at any context
 // length. Every warp walks every tile for the ring protocol.
@@ -685,35 +678,31 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
     constexpr int NHG = KV_MUL / HW;            // head groups per KV head
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* sq = sh.scr;
-    int nc, u0, u1;
-    attn_units(p, nc, u0, u1);
     float* fl = flow_layer(p, l);
     const float* qkv = fl + p.o_qkv;
     const float* gq = p.q_norm + (size_t) l * 128;
     const float* gk = p.k_norm + (size_t) l * 128;
     const unsigned it_base = it;
-    const unsigned U = (unsigned) (p.KVHl * nc);
+    const AttnSplit as = attn_split(p);
+    const int kvh = as.kvh, my_slot = as.j;
+    const int npos = as.p_hi - as.p_lo;                          // cached positions of this block
+    const int ntile = (npos + kChunk - 1) / kChunk;
+    const bool own_last = as.j == as.n - 1;                      // this block also takes the step's own position
     const int hg = warp % NHG;                                   // this warp's head group
     const int wi = warp / NHG;                                   // its index among the warps of the group
     const int wn = (kConsumerWarps - hg + NHG - 1) / NHG;        // warps in the group
 
-    if (u0 == u1 && (unsigned) u0 < U && warp == 0 && lane < KV_MUL) {
-        // no tiles here (short context): if this block lies between the first and last block of a KV head,
-        // the head's combine tasks expect its (m, l)
-        const int kvh = u0 / nc, b = my_block(p.perm);
-        const int blo = block_of_unit((unsigned) (kvh * nc), U, gridDim.x), bhi = block_of_unit((unsigned) (kvh * nc + nc - 1), U, gridDim.x);
-        if (b > blo && b < bhi) {
-            float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + (b - blo)) * KV_MUL + lane) * kPartStride;
+    if (npos == 0 && !own_last) {
+        // nothing to attend over here (short context): the kv head's combine tasks still expect this block's (m, l)
+        if (warp == 0 && lane < KV_MUL) {
+            float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + my_slot) * KV_MUL + lane) * kPartStride;
             stf_f32(dst + 128, -INFINITY);
             stf_f32(dst + 129, 0.0f);
             __threadfence();
         }
+        return;
     }
-    int u = u0;
-    while (u < u1) {
-        const int kvh = u / nc;
-        const int seg_end = min(u1, (kvh + 1) * nc);
-        const bool own_last = seg_end == (kvh + 1) * nc; // the segment contains the KV head's last chunk
+    {
         // ---- segment prologue: warp j < KV_MUL prepares query head j; warps KV_MUL, KV_MUL+1 this step's K, V row
         bar_consumers(); // previous users of the scratch are done
         if (warp < KV_MUL + (own_last ? 2 : 0)) {
@@ -744,9 +733,6 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
         // ---- tiles, in groups of kGroupTiles: the warps of a head group split the cached positions of a
         // group into equal contiguous ranges (<= 2 tiles each), so all warps work on every group at once and
         // the ring keeps flowing (splitting the whole segment contiguously serialised the warps behind it)
-        const int ntile = seg_end - u;
-        const int pbase = (u - kvh * nc) * kChunk;                           // first position of the segment
-        const int npos = max(0, min(p.pos, pbase + ntile * kChunk) - pbase); // cached positions in the segment
         float4 q[HW];
 #pragma unroll
         for (int j = 0; j < HW; ++j) q[j] = *reinterpret_cast<const float4*>(sq + (hg * HW + j) * 128 + lane * 4);
@@ -761,7 +747,7 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
             int cnta = 0;
 #pragma unroll 1
             for (int t = 0; t < gt; ++t) {
-                const unsigned itx = it_base + (unsigned) (u - u0 + g0 + t);
+                const unsigned itx = it_base + (unsigned) (g0 + t);
                 const unsigned slot = itx % p.nslot;
                 mbar_wait(sh, p, sh.full + slot * 8, (itx / p.nslot) & 1, 4);
                 const int a = max(my0, t * kChunk) - t * kChunk, b = min(my1, (t + 1) * kChunk) - t * kChunk;
@@ -795,9 +781,7 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
         }
         // ---- publish (m, l, acc) of this CTA for the segment's heads
         if (warp < NHG) {
-            const int blo = block_of_unit((unsigned) (kvh * nc), U, gridDim.x);
-            const int slot = my_block(p.perm) - blo;
-            float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + slot) * KV_MUL + warp * HW) * kPartStride;
+            float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + my_slot) * KV_MUL + warp * HW) * kPartStride;
 #pragma unroll
             for (int j = 0; j < HW; ++j) {
                 stf_f4(dst + j * kPartStride + lane * 4, st.acc[j]);
@@ -808,9 +792,8 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
             }
             __threadfence(); // flush (see consume_mat)
         }
-        u = seg_end;
     }
-    it = it_base + (unsigned) (u1 - u0);
+    it = it_base + (unsigned) ntile;
 }
 
 // Combine (CTA-wide): task t = (head h, half hf) merges the published partials of the head (online-
@@ -818,9 +801,8 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
 // the fp32 result (debug read-back) and the Q8_0 group -- 64 codes + scale -- straight into the flow
 // vector the wo GEMV loads. Task t runs on CTA t % grid with ALL its warps: thread (dim = tid & 63,
 // slot group = tid >> 6) takes slots sg, sg + 7, ...; every load of the task is in flight at once, so
-// the task costs one L2 round trip plus a shared-memory reduction. Every block between the first and
-// last block of a KV head publishes (m, l) -- blocks without tiles publish (-inf, 0) -- so no slot of
-// the range stays unwritten.
+// the task costs one L2 round trip plus a shared-memory reduction. Every block of a KV head publishes
+// (m, l) -- blocks without tiles publish (-inf, 0) -- so no slot of the range stays unwritten.
 __device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams& p, int l) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntask = 2 * p.Hl;
@@ -829,26 +811,81 @@ __device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams&
     float* mm = sh.scr;        // [<= kMaxGrid] slot maxima, then slot weights
     float* ll = sh.scr + 256;  // [<= kMaxGrid] slot sums
     float* red = sh.scr + 512; // [7][64] partial outputs per slot group
-    const int nc = p.pos / kChunk + 1;
-    const unsigned U = (unsigned) (p.KVHl * nc);
 #pragma unroll 1
     for (int t = blockIdx.x; t < ntask; t += G) {
         const int h = t >> 1, hf = t & 1, kvh = h / p.kv_mul;
-        const unsigned ulo = (unsigned) (kvh * nc);
-        const int blo = block_of_unit(ulo, U, G), nb = block_of_unit(ulo + nc - 1, U, G) - blo + 1;
+        const int nb = (int) ((kvh + 1) * G / p.KVHl - kvh * G / p.KVHl); // blocks of the kv head: all of them publish
         const float* part = fl + p.o_part + ((size_t) kvh * p.part_slots * p.kv_mul + h % p.kv_mul) * kPartStride;
         const size_t ss = (size_t) p.kv_mul * kPartStride; // between slots
         const int d = hf * 64 + (tid & 63), sg = tid >> 6;
         bar_consumers(); // scratch free (attention merge / previous task)
-        float a[3];
+        // Thread (dim, slot group) needs the accumulator word of slots sg, sg + 7, sg + 14 -- but a slot whose maximum is
+        // -inf never gets an accumulator, so the thread polls (m, acc) of each of its slots TOGETHER and is done with a
+        // slot once m is there and either m == -inf or acc is there. Everything the task needs is in flight at once and is
+        // noticed one round trip after it lands (polling acc only after m had landed cost up to 3 serial round trips).
+        float a[3], ms[3];
+        bool pend[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { // speculative: issued before the weights are known
-            const int i = sg + 7 * k;
-            a[k] = (sg < 7 && i < nb) ? __uint_as_float(ldf_u32(part + i * ss + d)) : 0.0f;
+        for (int k = 0; k < 3; ++k) {
+            pend[k] = sg < 7 && sg + 7 * k < nb;
+            a[k] = 0.0f;
+            ms[k] = -INFINITY;
+        }
+        bool pend_ml = tid < nb;
+        float my_m = -INFINITY, my_l = 0.0f;
+        {
+            unsigned long long t_start = 0;
+#pragma unroll 1
+            for (unsigned n = 1;; ++n) {
+                uint32_t wm[3], wa[3], w_m = 0, w_l = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (pend[k]) {
+                        wm[k] = ldf_u32(part + (sg + 7 * k) * ss + 128);
+                        wa[k] = ldf_u32(part + (sg + 7 * k) * ss + d);
+                    }
+                if (pend_ml) {
+                    w_m = ldf_u32(part + tid * ss + 128);
+                    w_l = ldf_u32(part + tid * ss + 129);
+                }
+                bool busy = false;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (pend[k]) {
+                        const float mk = __uint_as_float(wm[k]);
+                        if (wm[k] != kSent && (mk == -INFINITY || wa[k] != kSent)) {
+                            ms[k] = mk;
+                            a[k] = mk == -INFINITY ? 0.0f : __uint_as_float(wa[k]);
+                            pend[k] = false;
+                        } else {
+                            busy = true;
+                        }
+                    }
+                if (pend_ml) {
+                    if (w_m != kSent && w_l != kSent) {
+                        my_m = __uint_as_float(w_m);
+                        my_l = __uint_as_float(w_l);
+                        pend_ml = false;
+                    } else {
+                        busy = true;
+                    }
+                }
+                if (!busy) break;
+                if ((n & 255u) == 0) {
+                    if (*sh.abort_flag) break;
+                    const unsigned long long now = gtime_ns();
+                    if (t_start == 0) t_start = now;
+                    if (now - t_start > kTimeoutNs) {
+                        *sh.abort_flag = 14;
+                        *p.err = 14;
+                        break;
+                    }
+                }
+            }
         }
         if (tid < nb) {
-            mm[tid] = poll1(sh, p, part + tid * ss + 128, 14);
-            ll[tid] = poll1(sh, p, part + tid * ss + 129, 14);
+            mm[tid] = my_m;
+            ll[tid] = my_l;
         }
         bar_consumers();
         float M = -INFINITY;
@@ -864,8 +901,8 @@ __device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams&
                     if (i >= nb) continue;
                     const float m = mm[i];
                     if (m == -INFINITY) continue; // nothing attended there: its accumulator is not even written
-                    float v = i0 == sg ? a[k] : __uint_as_float(ldf_u32(part + i * ss + d));
-                    if (__float_as_uint(v) == kSent) v = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + i * ss + d, 14));
+                    float v = a[k]; // slots sg .. sg + 14 were fetched above; further ones (> 21 slots per KV head) here
+                    if (i0 != sg) v = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + i * ss + d, 14));
                     A = __fmaf_rn(v, expf(__fsub_rn(m, M)), A);
                 }
             }
@@ -1103,6 +1140,11 @@ int qw_mega_init(QwenCudaCtx* c) {
         return -1;
     }
     st->grid = std::min(c->num_sms, kMaxGrid);
+    if (st->grid < c->KVHl) { // every kv head needs a block of its own (attn_split)
+        st->grid = 0;
+        c->path = 1;
+        return 0;
+    }
     {
         auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
         int k = std::max(1, st->grid / 3);
@@ -1119,7 +1161,7 @@ int qw_mega_init(QwenCudaCtx* c) {
         st->o_qkv = (int) o; o += up4((size_t) c->Pl + 2 * c->Kl);
         st->o_h = (int) o; o += up4(c->Hdl);
         st->o_attq = (int) o; o += up4(qw_row_bytes(c->Pl) / 4);
-        st->part_slots = std::min(st->grid, st->grid / c->KVHl + 2);
+        st->part_slots = st->grid / c->KVHl + 1; // blocks per kv head (attn_split): floor or ceil of grid / KVH
         st->o_part = (int) o; o += up4((size_t) c->KVHl * st->part_slots * kv_mul * kPartStride);
         st->layer_words = o;
         st->x0_off = o * c->L; // after the layers: the embedding row
