@@ -502,3 +502,20 @@ def test_prefill_in_two_calls_equals_one_call(qlib, pkg, ckpt_dir):
         g2.forward_prefill(prompt[:33], 0)
         b = g2.forward_prefill(prompt[33:], 33)
         same(a, b)
+
+
+def test_persistent_kernel_is_deterministic(qlib, pkg, ckpt_dir):
+    """No atomics on data, static work split: the same tokens give bit-identical logits in two independent contexts
+    (different arrival orders at every hand-off) and when a context replays the same positions."""
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "4b-l2", seed=11)
+    toks = [3, 1415, 926, 535, 897, 932, 384, 626]
+    runs = []
+    for _ in range(2):
+        with qlib.open(path, 64) as gm:
+            a = [gm.forward(t, pos) for pos, t in enumerate(toks)]
+            b = [gm.forward(t, pos) for pos, t in enumerate(toks)]  # replay: overwrites the same KV rows with the same values
+            for x, y in zip(a, b):
+                same(x, y)
+            runs.append(a)
+    for x, y in zip(*runs):
+        same(x, y)
