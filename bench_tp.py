@@ -64,14 +64,17 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
         bytes_tok = float(np.mean([shape.decode_bytes(ctx + W + i) for i in range(K)]))
         peak, peak_src = measured_peak()
         achieved = bytes_tok / world * tok_s / 1e9  # per-GPU share of the algorithmic bytes
+        fused = gm.get_path() == 0
         line = dict(base, value=tok_s, ms_per_step=ms / K, dtype="int8xint8->int32, fp32", clocks=clocks,
-                    gpu_launches=launches + K * (2 * shape.n_layers + 1),
+                    gpu_launches=launches if fused else launches + K * (2 * shape.n_layers + 1),
                     e2e={"value": K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": shape.vocab_size * 4},
                     roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                               "traffic": None, "peak_source": peak_src, "bytes_per_token": bytes_tok,
-                              "kernel": "per-op kernels + NCCL all-reduce (the persistent kernel is single-GPU in round 1)"})
+                              "kernel": ("k_decode (persistent, 1 launch/token/rank; all-reduce fused into the wo / w2 epilogues as NVLink "
+                                         "peer stores) + 1 ncclAllGather of the logits") if fused
+                              else "per-op kernels + NCCL all-reduce (peer mapping unavailable)"})
         line["config"]["parallelism"] = f"tp{world}"
-        line["config"]["path"] = "ops+nccl"
+        line["config"]["path"] = "mega+peer-stores" if fused else "ops+nccl"
         print(json.dumps(line), flush=True)
     gm.close()
     dist.barrier()

@@ -80,7 +80,12 @@ void qwen_cuda_destroy(QwenCudaCtx* ctx);
 
 /* Tensor parallelism, one process per GPU (no reference counterpart: the reference is single
  * process). Rank 0 makes an id, the caller's own rendezvous hands the same 128
- * bytes to every rank, each rank then joins. Contexts with tp.size == 1 need neither. */
+ * bytes to every rank, each rank then joins. Contexts with tp.size == 1 need neither.
+ * qwen_cuda_tp_init also exchanges cudaIpc handles of the persistent kernel's flow arenas through the
+ * new communicator and maps every peer's arena (NVLink peer access): the all-reduce after wo / w2 then
+ * happens INSIDE the persistent kernel (each rank's GEMV epilogue stores its partial sums into every
+ * rank's arena, readers add them in rank order). Without peer access the context stays on the per-op
+ * kernels + ncclAllReduce path. */
 int qwen_cuda_tp_unique_id(void* out128);
 int qwen_cuda_tp_init(QwenCudaCtx* ctx, const void* id128);
 
@@ -115,6 +120,10 @@ int qwen_cuda_time_decode(QwenCudaCtx* ctx, int token, int pos0, int steps, int 
 int qwen_cuda_sync(QwenCudaCtx* ctx);
 /* 0 = persistent decode kernel (default), 1 = one kernel per op (debug / cross-check). */
 int qwen_cuda_set_path(QwenCudaCtx* ctx, int path);
+/* Which path the next step takes (0 / 1 as above; negative on a NULL context). Tensor-parallel contexts
+ * report 0 once qwen_cuda_tp_init has mapped the peers' flow arenas (the persistent kernel then does the
+ * all-reduce itself with NVLink peer stores), 1 if they fell back to per-op kernels + NCCL. */
+int qwen_cuda_get_path(const QwenCudaCtx* ctx);
 
 /* ---- KV cache access (test + long-context parity hooks) ----------------------
  * Host side uses the reference's order: [npos][n_kv_heads*head_dim] for one layer

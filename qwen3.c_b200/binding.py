@@ -103,6 +103,7 @@ class QwenLib:
         L.qwen_cuda_time_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_int32_p]
         L.qwen_cuda_sync.argtypes = [C.c_void_p]
         L.qwen_cuda_set_path.argtypes = [C.c_void_p, C.c_int]
+        L.qwen_cuda_get_path.argtypes = [C.c_void_p]
         L.qwen_cuda_kv_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_kv_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_debug_set_layers.argtypes = [C.c_void_p, C.c_int]
@@ -234,6 +235,9 @@ class B200Model:
 
     def set_path(self, path: int):
         self.ql._ok(self.ql.lib.qwen_cuda_set_path(self.ctx, path), "set_path")
+
+    def get_path(self) -> int:
+        return int(self.ql.lib.qwen_cuda_get_path(self.ctx))
 
     def set_layers(self, n: int):
         self.ql._ok(self.ql.lib.qwen_cuda_debug_set_layers(self.ctx, n), "set_layers")

@@ -244,6 +244,7 @@ int qw_mega_profile_enable(QwenCudaCtx* c);
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems);
 int qw_mega_tlog(QwenCudaCtx* c, int warp, unsigned long long* host);
 int qw_mega_reset(QwenCudaCtx* c);
+bool qw_mega_tp_ready(const QwenCudaCtx* c);
 const float* qw_mega_debug_ptr(QwenCudaCtx* c, const char* what);
 extern "C" int qwen_cuda_debug_tile_log(QwenCudaCtx* c, int warp, unsigned long long* host) { return c ? qw_mega_tlog(c, warp, host) : -2; }
 extern "C" int qwen_cuda_debug_profile_enable(QwenCudaCtx* c) { return c ? qw_mega_profile_enable(c) : -2; }
@@ -287,13 +288,15 @@ extern "C" int qwen_cuda_debug_set_layers(QwenCudaCtx* c, int n) {
 
 extern "C" int qwen_cuda_set_path(QwenCudaCtx* c, int path) {
     if (!c || path < 0 || path > 1) return -2;
-    if (path == 0 && c->tp_size != 1) {
-        qw_set_error("persistent kernel path is single-GPU only");
+    if (path == 0 && !qw_mega_tp_ready(c)) {
+        qw_set_error("persistent kernel path: the peers' flow arenas are not mapped (qwen_cuda_tp_init) or the shape is unsupported");
         return -2;
     }
     c->path = path;
     return 0;
 }
+
+extern "C" int qwen_cuda_get_path(const QwenCudaCtx* c) { return c ? c->path : -2; }
 
 static int step(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     if (pos < 0 || pos >= c->S) {

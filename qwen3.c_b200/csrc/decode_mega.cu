@@ -35,8 +35,10 @@
 // Every wait in this file has a wall-clock timeout that raises a sticky error flag
 // instead of hanging the GPU.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "attn_core.cuh"
@@ -50,7 +52,8 @@ constexpr int kSlotBytes = 28672;           // one ring slot: 105 SG records or 
 constexpr int kChunk = 28;                  // KV positions per attention tile (2*28*512 B = one slot)
 constexpr int kMaxSlots = 8;
 constexpr int kMaxGrid = 256;
-constexpr unsigned long long kTimeoutNs = 2000000000ull;
+constexpr unsigned long long kTimeoutNs = 4000000000ull; // also covers the launch skew between tensor-parallel ranks
+constexpr int kMaxTp = 8;
 constexpr int kProfSlots = 16;              // per layer: stamps after each phase step (CTA-local, thread 0)
 constexpr uint32_t kSent = 0x7F808080u;     // "not written yet": sNaN as fp32, contains code -128 as int8x4
 constexpr int kGroupTiles = 4;              // attention tiles the 15 warps work on together
@@ -62,7 +65,8 @@ struct MatDesc {
     size_t stride;       // bytes between layers
     int rows, n, gran;   // rows, columns, granularity of the per-CTA row split
     int rt;              // rows per ring tile
-    int kind;            // epilogue: 0 out[row] = v, 1 out[row] = resid[row] + v, 2 out[row/2] = silu(v0) * v1
+    int kind;            // epilogue: 0 out[row] = v, 1 out[row] = resid[row] + v, 2 out[row/2] = silu(v0) * v1,
+                         // 3 tensor parallel: this rank's partial v goes to slot tp_rank of EVERY rank's arena (peer stores)
 };
 
 struct MegaParams {
@@ -85,6 +89,13 @@ struct MegaParams {
     int* err;
     unsigned long long* prof; // optional [CTA][L+1][kProfSlots] globaltimer stamps (debug)
     int nslot, off_xq, off_scr, off_misc, off_bar;
+    // tensor parallelism (one process per GPU): the all-reduce after wo / w2 is fused into the GEMV epilogue as
+    // peer stores over NVLink into every rank's flow arena; readers add the tp partials in rank order
+    int tp, tp_rank;
+    int attn_ga;        // blocks that take part in attention (<= grid): min(grid, cap * KVHl)
+    int part_stride;    // words between the per-rank partial vectors of xa / xb
+    int off_xres;       // shared memory: the fp32 residual stream, kept by every CTA (tp > 1 only)
+    float* peer_flow[kMaxTp]; // this launch's arena on every rank (own entry = flow)
 };
 
 struct MegaState {
@@ -96,7 +107,10 @@ struct MegaState {
     int grid = 0, nslot = 0, dbg_mode = 0, perm = 1, l2_ahead = 0;
     unsigned long long* prof = nullptr;
     size_t smem = 0;
-    int off_xq, off_scr, off_misc, off_bar;
+    int off_xq, off_scr, off_misc, off_bar, off_xres = 0;
+    int attn_ga = 0, part_stride = 0;
+    float* peer[2][kMaxTp] = {};  // mapped arenas of every rank (cudaIpc), [parity][rank]; own entries = arena[parity]
+    bool peers_open = false;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -154,11 +168,21 @@ __device__ __forceinline__ void stf_u32(void* p, uint32_t v) {
 __device__ __forceinline__ void stf_f4(float* p, const float4& v) {
     asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// tensor-parallel partials: written by peer GPUs over NVLink, so system scope on both sides
+__device__ __forceinline__ void stf_sys_f32(float* p, float v) {
+    asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldf_sys_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ bool unset4(const uint4& v) { return v.x == kSent || v.y == kSent || v.z == kSent || v.w == kSent; }
 
 struct Shared {
     uint8_t* ring;
     uint8_t* xq;   // activation vector in SG layout: [256 codes][4 scales] records
+    float* xres;   // tp > 1: the residual stream x[D], element i owned by the thread that quantises it
     float* scr;
     float* misc;
     uint32_t full, empty; // shared-space addresses of the barrier arrays
@@ -261,9 +285,12 @@ __device__ __forceinline__ void cta_rows(const MatDesc& m, int perm, int& r0, in
 struct AttnSplit {
     int kvh, j, n;   // kv head, index of this block among the kv head's n blocks
     int p_lo, p_hi;  // cached positions [p_lo, p_hi) of this block
+    bool active;     // false: this block takes no part in attention (tensor-parallel ranks with few kv heads
+                     // use at most p.attn_ga blocks, so a combine task never merges more than ~42 partials)
 };
 __device__ __forceinline__ AttnSplit attn_split(const MegaParams& p) {
-    const int G = gridDim.x, KVH = p.KVHl, b = my_block(p.perm);
+    const int G = p.attn_ga, KVH = p.KVHl, b = my_block(p.perm);
+    if (b >= G) return AttnSplit{0, 0, 0, 0, 0, false};
     int h = b * KVH / G;
     while ((h + 1) * G / KVH <= b) ++h;
     const int f0 = h * G / KVH;
@@ -273,6 +300,7 @@ __device__ __forceinline__ AttnSplit attn_split(const MegaParams& p) {
     a.n = (h + 1) * G / KVH - f0;
     a.p_lo = (int) ((long long) p.pos * a.j / a.n);
     a.p_hi = (int) ((long long) p.pos * (a.j + 1) / a.n);
+    a.active = true;
     return a;
 }
 
@@ -298,7 +326,7 @@ __device__ __noinline__ void prefetch_subphase(const MegaParams& p, int sp) {
     const int l = sp / 5, k = sp == nsp ? 5 : sp % 5;
     if (k == 1) {
         const AttnSplit a = attn_split(p);
-        if (a.p_hi > a.p_lo) {
+        if (a.active && a.p_hi > a.p_lo) {
             const size_t off = (((size_t) l * p.KVHl + a.kvh) * p.S + a.p_lo) * 128;
             prefetch_l2(reinterpret_cast<const uint8_t*>(p.k_cache + off), (size_t) (a.p_hi - a.p_lo) * 512);
             prefetch_l2(reinterpret_cast<const uint8_t*>(p.v_cache + off), (size_t) (a.p_hi - a.p_lo) * 512);
@@ -378,6 +406,9 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
 // No CTA-wide barrier per tile: warps meet only at the ring's mbarriers, so with one unit per
 // tile (n = 9728) different warps work on different ring slots at the same time.
 // kind 0: out[row] = v      kind 1: out[row] = resid[row] + v      kind 2: out[row/2] = silu(v0) * v1
+// kind 3 (tensor parallel, wo / w2): v is this rank's partial sum over its column window; lane 2q + j stores row j
+// of the unit into slot tp_rank of rank q's arena at BYTE offset `out` (st.relaxed.sys over NVLink; the
+// own rank is one of the q). That IS the all-reduce: the readers add the tp slots in rank order (prologue_quant).
 // `out` is a flow-arena vector (or the logits): each element is stored exactly once.
 __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& p, const MatDesc& m, int /*layer*/, unsigned& it, float* out, const float* resid) {
     int r0, r1;
@@ -459,6 +490,14 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
             }
             if (KIND == 2) {
                 if (lane == 0) stf_f32(out + (grow >> 1), __fmul_rn(silu_ref(acca), accb));
+            } else if (KIND == 3) {
+                if (lane < 2 * p.tp && ((lane & 1) == 0 || two)) {
+                    char* base = reinterpret_cast<char*>(p.peer_flow[0]);
+#pragma unroll
+                    for (int q = 1; q < kMaxTp; ++q) // static indices: a dynamic one makes a local copy of the parameter array
+                        if ((lane >> 1) == q) base = reinterpret_cast<char*>(p.peer_flow[q]);
+                    stf_sys_f32(reinterpret_cast<float*>(base + reinterpret_cast<size_t>(out)) + grow + (lane & 1), (lane & 1) ? accb : acca);
+                }
             } else if (lane < 2 && (lane == 0 || two)) {
                 const float v = lane == 0 ? acca : accb;
                 stf_f32(out + grow + lane, KIND == 1 ? __fadd_rn(xres, v) : v);
@@ -471,7 +510,7 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     }
     // push this warp's results out NOW: without a fence the stores sit in the SM's write path for
     // microseconds (measured, scripts/ubench/handoff.cu: 2.7 us per hand-off without, 1.05 us with)
-    __threadfence();
+    if (KIND == 3) __threadfence_system(); else __threadfence();
 }
 
 // ---------------------------------------------------------------- consumer: prologues
@@ -519,40 +558,124 @@ __device__ __forceinline__ void quant_record(uint8_t* xq, int rec, int lane, con
 
 constexpr int kRecBatch = 3; // records per warp and pass: 45 records = 11520 columns per pass
 
+// poll until the 4 words at q (written by a peer GPU) are all there
+__device__ __noinline__ uint4 poll4_sys_slow(volatile int* abort_flag, int* err, const void* q, int code) {
+    unsigned long long t0 = 0;
+    uint4 v = ldf_sys_u4(q);
+    for (unsigned n = 1; unset4(v); ++n) {
+        if ((n & 255u) == 0) {
+            if (*abort_flag) break;
+            const unsigned long long now = gtime_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kTimeoutNs) {
+                *abort_flag = code;
+                *err = code;
+                break;
+            }
+        }
+        v = ldf_sys_u4(q);
+    }
+    return v;
+}
+
+// Receiving half of the fused all-reduce (tensor parallel): x += part[0] + ... + part[nparts-1] for the elements of
+// the residual stream this thread owns (records warp, warp + 15, ...; 8 columns per lane), in rank order so that all
+// ranks hold bit-identical x. The partials were pushed into this rank's arena by every rank's wo / w2 epilogue.
+// Out of line: its registers must not add to the pressure of the kernel's main body.
+__device__ __noinline__ void tp_gather_x(float* xres, const float* src, int nparts, int part_stride, int recs, int groups,
+                                         volatile int* abort_flag, int* err) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int rec = warp; rec < recs; rec += kConsumerWarps) {
+        if (rec * 4 + (lane >> 3) >= groups) continue;
+        const int col = rec * 256 + lane * 8;
+        float4* xr = reinterpret_cast<float4*>(xres + col);
+        float4 x0 = xr[0], x1 = xr[1];
+#pragma unroll 1
+        for (int q0 = 0; q0 < nparts; q0 += 4) { // four ranks' partials in flight at once
+            uint4 a[4], b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (q0 + j < nparts) {
+                    const float* q = src + (size_t) (q0 + j) * part_stride + col;
+                    a[j] = ldf_sys_u4(q);
+                    b[j] = ldf_sys_u4(q + 4);
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (q0 + j < nparts) {
+                    const float* q = src + (size_t) (q0 + j) * part_stride + col;
+                    if (unset4(a[j])) a[j] = poll4_sys_slow(abort_flag, err, q, 15);
+                    if (unset4(b[j])) b[j] = poll4_sys_slow(abort_flag, err, q + 4, 15);
+                    x0.x = __fadd_rn(x0.x, __uint_as_float(a[j].x)); x0.y = __fadd_rn(x0.y, __uint_as_float(a[j].y));
+                    x0.z = __fadd_rn(x0.z, __uint_as_float(a[j].z)); x0.w = __fadd_rn(x0.w, __uint_as_float(a[j].w));
+                    x1.x = __fadd_rn(x1.x, __uint_as_float(b[j].x)); x1.y = __fadd_rn(x1.y, __uint_as_float(b[j].y));
+                    x1.z = __fadd_rn(x1.z, __uint_as_float(b[j].z)); x1.w = __fadd_rn(x1.w, __uint_as_float(b[j].w));
+                }
+        }
+        xr[0] = x0;
+        xr[1] = x1;
+    }
+}
+
 // fp32 flow vector src[n] (written by other CTAs, polled) -> optional RMSNorm with weights nw
 // (forward.c:254-259; nw == nullptr: none) -> Q8_0 codes + scales in shared memory (q8.c:5-30).
 // Warp w owns records w, w + 15, w + 30 of a pass; all loads of a pass are issued up front (one L2
 // round trip). With RMSNorm the vector must fit one pass (checked at init).
-__device__ __forceinline__ void prologue_quant(const Shared& sh, const MegaParams& p, const float* src, int n, const float* __restrict__ nw) {
+// nparts >= 0 (tensor parallel, n == D): the vector is the residual stream, which every CTA keeps in shared
+// memory (sh.xres, each element owned by the thread that quantises it): x += part[0] + ... + part[nparts-1],
+// the partial sums every rank pushed into this rank's arena (src + q * part_stride), added in rank order so
+// that all ranks hold bit-identical x. This is the receiving half of the fused all-reduce (forward.c:295-298,
+// 335-338 are the residual adds it replaces).
+__device__ __forceinline__ void prologue_quant(const Shared& sh, const MegaParams& p, const float* src, int n, const float* __restrict__ nw, int nparts) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int groups = n / 64, recs = qw_sg_per_row(n);
 #pragma unroll 1
     for (int pass0 = 0; pass0 < recs; pass0 += kRecBatch * kConsumerWarps) { // uniform over the CTA: it contains a barrier
         const int r0 = pass0 + warp;
         float v[kRecBatch][8];
-        uint4 a[kRecBatch], b[kRecBatch];
         bool live[kRecBatch];
 #pragma unroll
         for (int k = 0; k < kRecBatch; ++k) {
             const int rec = r0 + k * kConsumerWarps;
             live[k] = rec < recs && rec * 4 + (lane >> 3) < groups;
-            if (live[k]) {
-                a[k] = ldf_u4(src + rec * 256 + lane * 8);
-                b[k] = ldf_u4(src + rec * 256 + lane * 8 + 4);
-            }
         }
+        if (nparts < 0) {
+            uint4 a[kRecBatch], b[kRecBatch];
 #pragma unroll
-        for (int k = 0; k < kRecBatch; ++k) {
+            for (int k = 0; k < kRecBatch; ++k) {
+                const int rec = r0 + k * kConsumerWarps;
+                if (live[k]) {
+                    a[k] = ldf_u4(src + rec * 256 + lane * 8);
+                    b[k] = ldf_u4(src + rec * 256 + lane * 8 + 4);
+                }
+            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[k][i] = 0.0f;
-            if (live[k]) {
-                const float* q = src + (r0 + k * kConsumerWarps) * 256 + lane * 8;
-                if (unset4(a[k])) a[k] = poll4_slow(sh.abort_flag, p.err, q, 10);
-                if (unset4(b[k])) b[k] = poll4_slow(sh.abort_flag, p.err, q + 4, 10);
-                v[k][0] = __uint_as_float(a[k].x); v[k][1] = __uint_as_float(a[k].y);
-                v[k][2] = __uint_as_float(a[k].z); v[k][3] = __uint_as_float(a[k].w);
-                v[k][4] = __uint_as_float(b[k].x); v[k][5] = __uint_as_float(b[k].y);
-                v[k][6] = __uint_as_float(b[k].z); v[k][7] = __uint_as_float(b[k].w);
+            for (int k = 0; k < kRecBatch; ++k) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[k][i] = 0.0f;
+                if (live[k]) {
+                    const float* q = src + (r0 + k * kConsumerWarps) * 256 + lane * 8;
+                    if (unset4(a[k])) a[k] = poll4_slow(sh.abort_flag, p.err, q, 10);
+                    if (unset4(b[k])) b[k] = poll4_slow(sh.abort_flag, p.err, q + 4, 10);
+                    v[k][0] = __uint_as_float(a[k].x); v[k][1] = __uint_as_float(a[k].y);
+                    v[k][2] = __uint_as_float(a[k].z); v[k][3] = __uint_as_float(a[k].w);
+                    v[k][4] = __uint_as_float(b[k].x); v[k][5] = __uint_as_float(b[k].y);
+                    v[k][6] = __uint_as_float(b[k].z); v[k][7] = __uint_as_float(b[k].w);
+                }
+            }
+        } else {
+            if (nparts > 0) tp_gather_x(sh.xres, src, nparts, p.part_stride, recs, groups, sh.abort_flag, p.err);
+#pragma unroll
+            for (int k = 0; k < kRecBatch; ++k) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[k][i] = 0.0f;
+                if (!live[k]) continue;
+                const int col = (r0 + k * kConsumerWarps) * 256 + lane * 8;
+                const float4* xr = reinterpret_cast<const float4*>(sh.xres + col);
+                const float4 x0 = xr[0], x1 = xr[1];
+                v[k][0] = x0.x; v[k][1] = x0.y; v[k][2] = x0.z; v[k][3] = x0.w;
+                v[k][4] = x1.x; v[k][5] = x1.y; v[k][6] = x1.z; v[k][7] = x1.w;
             }
         }
         if (nw) {
@@ -684,6 +807,7 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
     const float* gk = p.k_norm + (size_t) l * 128;
     const unsigned it_base = it;
     const AttnSplit as = attn_split(p);
+    if (!as.active) return; // this block has no share of the attention (no tiles, no partial expected from it)
     const int kvh = as.kvh, my_slot = as.j;
     const int npos = as.p_hi - as.p_lo;                          // cached positions of this block
     const int ntile = (npos + kChunk - 1) / kChunk;
@@ -814,7 +938,7 @@ __device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams&
 #pragma unroll 1
     for (int t = blockIdx.x; t < ntask; t += G) {
         const int h = t >> 1, hf = t & 1, kvh = h / p.kv_mul;
-        const int nb = (int) ((kvh + 1) * G / p.KVHl - kvh * G / p.KVHl); // blocks of the kv head: all of them publish
+        const int nb = (kvh + 1) * p.attn_ga / p.KVHl - kvh * p.attn_ga / p.KVHl; // blocks of the kv head: all of them publish
         const float* part = fl + p.o_part + ((size_t) kvh * p.part_slots * p.kv_mul + h % p.kv_mul) * kPartStride;
         const size_t ss = (size_t) p.kv_mul * kPartStride; // between slots
         const int d = hf * 64 + (tid & 63), sg = tid >> 6;
@@ -895,15 +1019,27 @@ __device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams&
             float A = 0.0f;
 #pragma unroll 1
             for (int i0 = sg; i0 < nb; i0 += 21) {
+                if (i0 != sg) { // slots beyond the first 21 of the kv head (tensor-parallel ranks with 1-2 kv heads): three loads in flight
+                    uint32_t w[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int i = i0 + 7 * k;
+                        w[k] = (i < nb && mm[i] != -INFINITY) ? ldf_u32(part + i * ss + d) : 0u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int i = i0 + 7 * k;
+                        if (w[k] == kSent) w[k] = poll1_slow(sh.abort_flag, p.err, part + i * ss + d, 14);
+                        a[k] = __uint_as_float(w[k]);
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int i = i0 + 7 * k;
                     if (i >= nb) continue;
                     const float m = mm[i];
                     if (m == -INFINITY) continue; // nothing attended there: its accumulator is not even written
-                    float v = a[k]; // slots sg .. sg + 14 were fetched above; further ones (> 21 slots per KV head) here
-                    if (i0 != sg) v = __uint_as_float(poll1_slow(sh.abort_flag, p.err, part + i * ss + d, 14));
-                    A = __fmaf_rn(v, expf(__fsub_rn(m, M)), A);
+                    A = __fmaf_rn(a[k], expf(__fsub_rn(m, M)), A);
                 }
             }
             red[sg * 64 + (tid & 63)] = A;
@@ -959,8 +1095,9 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
     }
     // the residual stream starts as the dequantised embedding row (forward.c:237): every CTA
     // contributes its slice of it to the flow vector x0
-    {
-        const int tok = p.token_dev ? *p.token_dev : p.token;
+    const bool tp = p.tp > 1;
+    const int tok = p.token_dev ? *p.token_dev : p.token;
+    if (!tp) {
         const uint8_t* row = p.w_emb + (size_t) tok * qw_row_bytes(p.D);
         const int c0 = (int) ((unsigned) p.D * blockIdx.x / gridDim.x), c1 = (int) ((unsigned) p.D * (blockIdx.x + 1) / gridDim.x);
 #pragma unroll 1
@@ -970,9 +1107,29 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
             stf_f32(p.flow_x0 + c, __fmul_rn((float) reinterpret_cast<const int8_t*>(rec)[c & 255], sc));
         }
         __threadfence();
+    } else {
+        // tensor parallel: every CTA keeps the whole residual stream in shared memory; each thread dequantises the
+        // elements it owns in prologue_quant (records warp, warp + 15, warp + 30; 8 columns per lane)
+        const uint8_t* row = p.w_emb + (size_t) tok * qw_row_bytes(p.D);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int recs = qw_sg_per_row(p.D), groups = p.D / 64;
+#pragma unroll 1
+        for (int rec = warp; rec < recs; rec += kConsumerWarps) {
+            if (rec * 4 + (lane >> 3) >= groups) continue;
+            const uint8_t* r = row + (size_t) rec * QW_SG_BYTES;
+            const uint2 cw = *reinterpret_cast<const uint2*>(r + lane * 8);
+            const float sc = *reinterpret_cast<const float*>(r + 256 + (lane >> 3) * 4);
+            float* xr = sh.xres + rec * 256 + lane * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int code = (int) (int8_t) (((i < 4 ? cw.x : cw.y) >> (8 * (i & 3))) & 0xffu);
+                xr[i] = __fmul_rn((float) code, sc);
+            }
+        }
     }
     unsigned it = 0;
-    const float* xprev = p.flow_x0; // residual stream entering the layer
+    const float* xprev = p.flow_x0; // residual stream entering the layer (tp: the last w2's per-rank partials, or null)
+    if (tp) xprev = nullptr;
     const int nph = 4 * p.layers_run;
 #pragma unroll 1
     for (int ph = 0; ph <= nph; ++ph) {
@@ -990,19 +1147,24 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
             prologue_load_codes(sh, p, reinterpret_cast<const uint8_t*>(fl + p.o_attq), p.Pl);
             out = fl + p.o_xa;
             resid = xprev;
+            if (tp) out = reinterpret_cast<float*>(4 * ((size_t) l * p.flow_layer_words + p.o_xa + (size_t) p.tp_rank * p.part_stride)); // kind 3: byte offset
         } else {
             const float *src, *nw;
-            int n = p.D;
+            int n = p.D, nparts = -1;
             if (k == 0) { // forward.c:254-259
                 src = xprev; nw = p.att_norm + (size_t) l * p.D; out = fl + p.o_qkv;
+                if (tp) nparts = xprev ? p.tp : 0;
             } else if (k == 2) { // forward.c:303-318
                 src = fl + p.o_xa; nw = p.ffn_norm + (size_t) l * p.D; out = fl + p.o_h;
+                if (tp) nparts = p.tp;
             } else if (k == 3) { // forward.c:319-338
                 src = fl + p.o_h; nw = nullptr; n = p.Hdl; out = fl + p.o_xb; resid = fl + p.o_xa;
+                if (tp) out = reinterpret_cast<float*>(4 * ((size_t) l * p.flow_layer_words + p.o_xb + (size_t) p.tp_rank * p.part_stride)); // kind 3: byte offset
             } else { // final norm + classifier (forward.c:344-348)
                 src = xprev; nw = p.out_norm; out = p.logits;
+                if (tp) nparts = xprev ? p.tp : 0;
             }
-            prologue_quant(sh, p, src, n, nw);
+            prologue_quant(sh, p, src, n, nw, nparts);
         }
         stamp(p, lp, 4 * (k & 3) + 2);
         consume_mat(sh, p, p.mat[k], l, it, out, resid);
@@ -1020,6 +1182,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ 
     sh.ring = smem;
     sh.xq = smem + p.off_xq;
     sh.scr = reinterpret_cast<float*>(smem + p.off_scr);
+    sh.xres = reinterpret_cast<float*>(smem + p.off_xres);
     sh.misc = reinterpret_cast<float*>(smem + p.off_misc);
     sh.full = smem_u32(smem + p.off_bar);
     sh.empty = sh.full + kMaxSlots * 8;
@@ -1084,8 +1247,8 @@ int qw_mega_init(QwenCudaCtx* c) {
     MegaState* st = new MegaState();
     c->mega = st;
     const int kv_mul = c->KVHl > 0 ? c->Hl / c->KVHl : 0;
-    if (c->tp_size != 1 || !(kv_mul == 1 || kv_mul == 2 || kv_mul == 4 || kv_mul == 8) || kv_mul * c->KVHl != c->Hl) {
-        c->path = 1; // tensor-parallel contexts and unusual head ratios use the per-op path
+    if (c->tp_size > kMaxTp || !(kv_mul == 1 || kv_mul == 2 || kv_mul == 4 || kv_mul == 8) || kv_mul * c->KVHl != c->Hl) {
+        c->path = 1; // unusual head ratios use the per-op path
         return 0;
     }
     const int amax = qw_pad_cols(std::max(c->D, std::max(c->Pl, c->Hdl)));
@@ -1115,7 +1278,9 @@ int qw_mega_init(QwenCudaCtx* c) {
     const int xq_b = (int) qw_row_bytes(amax);
     const int scr_b = std::max(kScrFloats, (kv_mul + 2) * 128) * 4;
     const int misc_b = 1024, bar_b = 2 * kMaxSlots * 8;
-    const int fixed = ((xq_b + 127) & ~127) + ((scr_b + 127) & ~127) + ((misc_b + 127) & ~127) + ((bar_b + 127) & ~127);
+    const int xres_b = c->tp_size > 1 ? qw_pad_cols(c->D) * 4 : 0; // tensor parallel: the residual stream lives in every CTA
+    const int fixed = ((xq_b + 127) & ~127) + ((scr_b + 127) & ~127) + ((misc_b + 127) & ~127) + ((bar_b + 127) & ~127)
+                      + ((xres_b + 127) & ~127);
     const int avail = dev_smem - fixed - 1024; // 1 KB left for static shared + driver reserve
     st->nslot = std::min(kMaxSlots, avail / kSlotBytes);
     if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(st->nslot, atoi(e)));
@@ -1131,6 +1296,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     st->off_scr = take(scr_b);
     st->off_misc = take(misc_b);
     st->off_bar = take(bar_b);
+    st->off_xres = take(xres_b);
     st->smem = off;
     QW_CUDA(cudaFuncSetAttribute(decode_kernel(kv_mul), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
     int per_sm = 0;
@@ -1152,29 +1318,112 @@ int qw_mega_init(QwenCudaCtx* c) {
         st->perm = k;
         if (const char* e = getenv("QWEN_MEGA_PERM")) { const int v = atoi(e); if (v > 0 && gcd(v, st->grid) == 1) st->perm = v; }
     }
-    // flow arena: per layer [xa D][xb D][qkv P+2K][h Hd][attq row_bytes(P)/4][partials KVH x slots x kv_mul x 132]
+    // blocks per kv head in attention: all of them on one GPU (18-19 for 8 kv heads); tensor-parallel ranks with 1-2 kv
+    // heads are capped so that a combine task merges at most 2 x 21 partials
+    {
+        int cap = 42;
+        if (const char* e = getenv("QWEN_MEGA_ATTN_CAP")) cap = std::max(1, atoi(e));
+        st->attn_ga = (int) std::min<long long>(st->grid, (long long) cap * c->KVHl);
+    }
+    // flow arena: per layer [xa tp x D][xb tp x D][qkv P+2K][h Hd][attq row_bytes(P)/4][partials KVH x slots x kv_mul x 132]
+    // (tp > 1: xa / xb hold one partial vector per rank, written by that rank over NVLink)
     {
         auto up4 = [](size_t w) { return (w + 3) & ~(size_t) 3; };
         size_t o = 0;
-        st->o_xa = (int) o; o += up4(c->D);
-        st->o_xb = (int) o; o += up4(c->D);
+        st->part_stride = (int) up4(c->D);
+        st->o_xa = (int) o; o += (size_t) c->tp_size * st->part_stride;
+        st->o_xb = (int) o; o += (size_t) c->tp_size * st->part_stride;
         st->o_qkv = (int) o; o += up4((size_t) c->Pl + 2 * c->Kl);
         st->o_h = (int) o; o += up4(c->Hdl);
         st->o_attq = (int) o; o += up4(qw_row_bytes(c->Pl) / 4);
-        st->part_slots = st->grid / c->KVHl + 1; // blocks per kv head (attn_split): floor or ceil of grid / KVH
+        st->part_slots = st->attn_ga / c->KVHl + 1; // blocks per kv head (attn_split): floor or ceil of attn_ga / KVH
         st->o_part = (int) o; o += up4((size_t) c->KVHl * st->part_slots * kv_mul * kPartStride);
         st->layer_words = o;
         st->x0_off = o * c->L; // after the layers: the embedding row
         st->words = o * c->L + up4(c->D);
         for (int s = 0; s < 2; ++s) QW_CUDA(cudaMalloc((void**) &st->arena[s], st->words * 4));
     }
-    c->path = 0;
+    // tensor-parallel contexts run the per-op path until qw_mega_tp_connect has mapped the peers' arenas
+    c->path = c->tp_size > 1 ? 1 : 0;
+    for (int s = 0; s < 2; ++s) st->peer[s][c->tp_rank] = st->arena[s];
     return qw_mega_reset(c);
+}
+
+// Tensor parallelism, one process per GPU: exchange cudaIpc handles of the two flow arenas through the NCCL
+// communicator and map every peer's arenas into this process (NVLink peer access). After this the persistent
+// kernel's wo / w2 epilogues store their partial sums straight into every rank's arena -- the all-reduce is part
+// of the kernel. Returns 0 and leaves the context on the per-op + NCCL path if peer mapping is not possible.
+int qw_mega_tp_connect(QwenCudaCtx* c) {
+    MegaState* st = state_of(c);
+    if (!st || !st->grid || c->tp_size <= 1 || st->peers_open) return 0;
+    if (getenv("QWEN_TP_NO_PEER")) return 0;
+    const int tp = c->tp_size;
+    struct Rec { cudaIpcMemHandle_t h[2]; int ok; int pad[31]; };
+    static_assert(sizeof(Rec) == 2 * 64 + 128, "handle record");
+    Rec mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = cudaIpcGetMemHandle(&mine.h[0], st->arena[0]) == cudaSuccess
+              && cudaIpcGetMemHandle(&mine.h[1], st->arena[1]) == cudaSuccess;
+    cudaGetLastError();
+    Rec* dev = nullptr;
+    std::vector<Rec> all(tp);
+    QW_CUDA(cudaMalloc((void**) &dev, sizeof(Rec) * (tp + 1)));
+    QW_CUDA(cudaMemcpyAsync(dev + tp, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    if (qw_tp_allgather(c, reinterpret_cast<const float*>(dev + tp), reinterpret_cast<float*>(dev), sizeof(Rec) / 4)) return -1;
+    QW_CUDA(cudaMemcpyAsync(all.data(), dev, sizeof(Rec) * tp, cudaMemcpyDeviceToHost, c->stream));
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    bool ok = true;
+    for (int q = 0; q < tp; ++q) ok = ok && all[q].ok;
+    int opened = 0;
+    for (int q = 0; ok && q < tp; ++q) {
+        if (q == c->tp_rank) continue;
+        for (int s = 0; s < 2; ++s) {
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[q].h[s], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                fprintf(stderr, "[TP] rank %d cannot map rank %d's arena: %s\n", c->tp_rank, q, cudaGetErrorString(cudaGetLastError()));
+                ok = false;
+                break;
+            }
+            st->peer[s][q] = reinterpret_cast<float*>(ptr);
+            ++opened;
+        }
+    }
+    // every rank must reach the same verdict: all-gather the outcome
+    float verdict = ok ? 1.0f : 0.0f;
+    QW_CUDA(cudaMemcpyAsync(reinterpret_cast<float*>(dev + tp), &verdict, 4, cudaMemcpyHostToDevice, c->stream));
+    if (qw_tp_allgather(c, reinterpret_cast<const float*>(dev + tp), reinterpret_cast<float*>(dev), 1)) return -1;
+    std::vector<float> verdicts(tp);
+    QW_CUDA(cudaMemcpyAsync(verdicts.data(), dev, 4 * tp, cudaMemcpyDeviceToHost, c->stream));
+    QW_CUDA(cudaStreamSynchronize(c->stream)); // also the barrier: every rank's arenas are initialised and mapped
+    cudaFree(dev);
+    for (int q = 0; q < tp; ++q) ok = ok && verdicts[q] == 1.0f;
+    if (!ok) {
+        for (int q = 0; q < tp; ++q)
+            for (int s = 0; s < 2; ++s)
+                if (q != c->tp_rank && st->peer[s][q]) {
+                    cudaIpcCloseMemHandle(st->peer[s][q]);
+                    st->peer[s][q] = nullptr;
+                }
+        cudaGetLastError();
+        if (c->tp_rank == 0) fprintf(stderr, "[TP] peer mapping unavailable: per-op kernels + NCCL all-reduce\n");
+        return 0;
+    }
+    (void) opened;
+    st->peers_open = true;
+    c->path = 0;
+    return 0;
+}
+bool qw_mega_tp_ready(const QwenCudaCtx* c) {
+    const MegaState* st = reinterpret_cast<const MegaState*>(c->mega);
+    return st && st->grid && (c->tp_size == 1 || st->peers_open);
 }
 
 void qw_mega_free(QwenCudaCtx* c) {
     MegaState* st = state_of(c);
     if (!st) return;
+    for (int q = 0; q < kMaxTp; ++q)
+        for (int s = 0; s < 2; ++s)
+            if (st->peers_open && q != c->tp_rank && st->peer[s][q]) cudaIpcCloseMemHandle(st->peer[s][q]);
     void* bufs[] = {st->arena[0], st->arena[1], st->prof};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -1184,11 +1433,15 @@ void qw_mega_free(QwenCudaCtx* c) {
 
 int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     MegaState* st = state_of(c);
-    if (!st || !st->grid) {
+    if (!st || !st->grid || (c->tp_size > 1 && !st->peers_open)) {
         qw_set_error("persistent decode kernel is not initialised for this context");
         return -4;
     }
     MegaParams p;
+    memset(&p, 0, sizeof p);
+    p.tp = c->tp_size; p.tp_rank = c->tp_rank;
+    p.attn_ga = st->attn_ga; p.part_stride = st->part_stride; p.off_xres = st->off_xres;
+    for (int q = 0; q < c->tp_size; ++q) p.peer_flow[q] = st->peer[st->launches & 1][q];
     p.D = c->D; p.Hdl = c->Hdl; p.L = c->L; p.Hl = c->Hl; p.KVHl = c->KVHl; p.Pl = c->Pl; p.Kl = c->Kl; p.Vl = c->Vl;
     p.S = c->S; p.kv_mul = c->Hl / c->KVHl;
     p.pos = pos; p.token = token; p.token_dev = token_dev;
@@ -1200,9 +1453,10 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         return MatDesc{base, stride, rows, n, gran, rt, kind};
     };
     p.mat[0] = desc(c->w_qkv, c->w_qkv_stride, c->Pl + 2 * c->Kl, c->D, 1, 0);
-    p.mat[1] = desc(c->w_o, c->w_o_stride, c->D, c->Pl, 1, 1);
+    const int kres = c->tp_size > 1 ? 3 : 1; // wo / w2 epilogue: residual add on one GPU, partial push under tensor parallelism
+    p.mat[1] = desc(c->w_o, c->w_o_stride, c->D, c->Pl, 1, kres);
     p.mat[2] = desc(c->w_13, c->w_13_stride, 2 * c->Hdl, c->D, 2, 2);
-    p.mat[3] = desc(c->w_2, c->w_2_stride, c->D, c->Hdl, 1, 1);
+    p.mat[3] = desc(c->w_2, c->w_2_stride, c->D, c->Hdl, 1, kres);
     p.mat[4] = desc(c->w_cls, 0, c->Vl, c->D, 1, 0);
     p.w_emb = c->w_emb;
     p.att_norm = c->att_norm; p.ffn_norm = c->ffn_norm; p.out_norm = c->out_norm; p.q_norm = c->q_norm; p.k_norm = c->k_norm;
@@ -1227,10 +1481,12 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
     st->last_layers = p.layers_run;
     ++st->launches;
+    // the classifier is split over vocabulary rows: gather the logits slices
+    if (c->tp_size > 1 && qw_tp_allgather(c, c->logits, c->logits_all, c->Vl)) return -1;
     return 0;
 }
 
-int qw_decode_mega_launches(const QwenCudaCtx*) { return 1; }
+int qw_decode_mega_launches(const QwenCudaCtx* c) { return c->tp_size > 1 ? 2 : 1; }
 
 // test hook behind qwen_cuda_debug_quantize_fused: x[n] (device) -> SG-layout codes + scales (device)
 void qw_mega_quant_records(const float* x, int n, uint8_t* sg, cudaStream_t st) {

@@ -7,6 +7,8 @@
 
 #include "common.cuh"
 
+int qw_mega_tp_connect(QwenCudaCtx* c);
+
 namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -74,7 +76,8 @@ extern "C" int qwen_cuda_tp_init(QwenCudaCtx* c, const void* id128) {
         return -1;
     }
     c->nccl_comm = comm;
-    return 0;
+    // map the peers' flow arenas: from here on the persistent kernel does the all-reduce itself (decode_mega.cu)
+    return qw_mega_tp_connect(c);
 }
 
 void qw_tp_free(QwenCudaCtx* c) {

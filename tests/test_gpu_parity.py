@@ -372,18 +372,19 @@ def test_06b_shape_logits_match_oracle(qlib, oracle, pkg, ckpt_dir):
 
 
 def test_tensor_parallel_2gpu_matches_single_gpu(qlib, pkg, ckpt_dir):
-    """TP=2 over NCCL (one process per GPU) against TP=1 on the same checkpoint and tokens: same
-    greedy tokens, logits within the flip-noise bound. Needs 2 visible GPUs (gpurun --gpus 2)."""
+    """TP=2 (one process per GPU) against the oracle on the same checkpoints and tokens, on the persistent kernel
+    with the all-reduce fused as NVLink peer stores AND on the per-op + NCCL path: same greedy tokens on every rank
+    and path, logits within the flip-noise bound, bit-identical across ranks. Needs 2 visible GPUs (gpurun --gpus 2)."""
     import subprocess
     import sys
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "small", seed=11)
+    paths = [pkg.checkpoint.ensure_checkpoint(ckpt_dir, "small", seed=11), pkg.checkpoint.ensure_checkpoint(ckpt_dir, "8b-l2", seed=11)]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29531",
-                          os.path.join(root, "tests", "tp_gpu_worker.py"), path],
+                          os.path.join(root, "tests", "tp_gpu_worker.py")] + paths,
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert out.returncode == 0 and "TP_GPU_OK" in out.stdout, out.stdout[-3000:]
 
@@ -453,7 +454,7 @@ def test_prefill_matmul_batch_bit_identical_to_reference_matmul(qlib, oracle, n,
     same(out, acc)
 
 
-@pytest.mark.parametrize("shape_name,n_prompt", [("tiny", 5), ("tiny-untied", 37), ("small", 150)])
+@pytest.mark.parametrize("shape_name,n_prompt", [("tiny", 5), ("tiny-untied", 37), ("small", 150), ("small", 600)])  # 600: two chunks
 def test_prefill_matches_reference_token_by_token(qlib, oracle, pkg, ckpt_dir, shape_name, n_prompt):
     """forward_prefill() (tcgen05 GEMMs + batched ops + causal attention, csrc/prefill.cu) must leave the
     device in the state n forward() calls of the reference leave it in: the last token's logits within
@@ -470,7 +471,10 @@ def test_prefill_matches_reference_token_by_token(qlib, oracle, pkg, ckpt_dir, s
             lo = om.forward(tok, pos)
         lg = gm.forward_prefill(prompt, 0)
         bad = np.abs(lg - lo) > 1e-2 + 1e-3 * np.abs(lo)
-        assert bad.mean() < 1e-3 and np.abs(lg - lo).max() < 0.05 * max(1.0, lo.std()), np.abs(lg - lo).max()
+        if n_prompt <= 200:
+            assert bad.mean() < 1e-3 and np.abs(lg - lo).max() < 0.05 * max(1.0, lo.std()), np.abs(lg - lo).max()
+        else:  # hundreds of re-quantised K/V rows behind the last token: one-code flips add up; a bug is O(1)
+            assert np.abs(lg - lo).max() < 0.1 * max(1.0, lo.std()), np.abs(lg - lo).max()
         nxt, margin = oracle.argmax(lo)
         assert int(np.argmax(lg)) == nxt or margin < 2e-2
         ok, ov = om.kv()  # [L][seq_len][kv_dim]
@@ -481,7 +485,8 @@ def test_prefill_matches_reference_token_by_token(qlib, oracle, pkg, ckpt_dir, s
                     close(got, want, rtol=1e-4, atol=1e-4)
                 else:  # deeper rows see re-quantised activations: a rare one-code flip moves a few values
                     d = np.abs(got - want)
-                    assert (d > 2e-3 + 2e-3 * np.abs(want)).mean() < 1e-2 and d.max() < 0.05 * max(1.0, want.std()), (layer, d.max())
+                    share = 1e-2 if n_prompt <= 200 else 5e-2  # long prompts: flips in earlier rows feed every later row's attention
+                    assert (d > 2e-3 + 2e-3 * np.abs(want)).mean() < share and d.max() < 0.05 * max(1.0, want.std()), (layer, d.max())
         tok = nxt
         for step in range(8):  # decode from the prefilled cache with the persistent kernel
             lg, lo = gm.forward(tok, n_prompt + step), om.forward(tok, n_prompt + step)
@@ -502,6 +507,17 @@ def test_prefill_in_two_calls_equals_one_call(qlib, pkg, ckpt_dir):
         g2.forward_prefill(prompt[:33], 0)
         b = g2.forward_prefill(prompt[33:], 33)
         same(a, b)
+    # across the internal 512-token chunk boundary: one call (512 + 88) == 200 + 400 == 599 + 1
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "small", seed=11)
+    long_prompt = [int(t) for t in np.random.default_rng(4).integers(0, pkg.checkpoint.SHAPES["small"].vocab_size, size=600)]
+    with qlib.open(path, 640) as g1, qlib.open(path, 640) as g2, qlib.open(path, 640) as g3:
+        a = g1.forward_prefill(long_prompt, 0)
+        g2.forward_prefill(long_prompt[:200], 0)
+        b = g2.forward_prefill(long_prompt[200:], 200)
+        g3.forward_prefill(long_prompt[:599], 0)
+        c = g3.forward_prefill(long_prompt[599:], 599)
+        same(a, b)
+        same(a, c)
 
 
 def test_persistent_kernel_is_deterministic(qlib, pkg, ckpt_dir):
@@ -519,3 +535,20 @@ def test_persistent_kernel_is_deterministic(qlib, pkg, ckpt_dir):
             runs.append(a)
     for x, y in zip(*runs):
         same(x, y)
+
+
+def test_4b_full_shape_first_tokens(qlib, oracle, pkg, ckpt_dir):
+    """The headline configuration's checkpoint (Qwen3-4B shape, 36 layers, vocabulary 151936, fast-mode weights as in
+    bench.py): the first decode steps of the persistent kernel and a 3-token forward_prefill against the oracle."""
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "4b", seed=1234, mode="fast")
+    toks = [7, 151935, 4711]
+    with qlib.open(path, 16) as gm, oracle.open(path, 16) as om:
+        ref = [om.forward(t, pos) for pos, t in enumerate(toks)]
+        for pos, t in enumerate(toks):
+            lg = gm.forward(t, pos)
+            assert np.abs(lg - ref[pos]).max() < 0.05 * max(1.0, ref[pos].std()), (pos, np.abs(lg - ref[pos]).max())
+            nxt, margin = oracle.argmax(ref[pos])
+            assert int(np.argmax(lg)) == nxt or margin < 2e-2
+    with qlib.open(path, 16) as gm:
+        lg = gm.forward_prefill(toks, 0)
+        assert np.abs(lg - ref[-1]).max() < 0.05 * max(1.0, ref[-1].std())
