@@ -410,6 +410,7 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
 // of the unit into slot tp_rank of rank q's arena at BYTE offset `out` (st.relaxed.sys over NVLink; the
 // own rank is one of the q). That IS the all-reduce: the readers add the tp slots in rank order (prologue_quant).
 // `out` is a flow-arena vector (or the logits): each element is stored exactly once.
+template <bool TP>
 __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& p, const MatDesc& m, int /*layer*/, unsigned& it, float* out, const float* resid) {
     int r0, r1;
     cta_rows(m, p.perm, r0, r1);
@@ -490,7 +491,7 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
             }
             if (KIND == 2) {
                 if (lane == 0) stf_f32(out + (grow >> 1), __fmul_rn(silu_ref(acca), accb));
-            } else if (KIND == 3) {
+            } else if (TP && KIND == 3) {
                 if (lane < 2 * p.tp && ((lane & 1) == 0 || two)) {
                     char* base = reinterpret_cast<char*>(p.peer_flow[0]);
 #pragma unroll
@@ -510,7 +511,7 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     }
     // push this warp's results out NOW: without a fence the stores sit in the SM's write path for
     // microseconds (measured, scripts/ubench/handoff.cu: 2.7 us per hand-off without, 1.05 us with)
-    if (KIND == 3) __threadfence_system(); else __threadfence();
+    if (TP && KIND == 3) __threadfence_system(); else __threadfence();
 }
 
 // ---------------------------------------------------------------- consumer: prologues
@@ -627,6 +628,7 @@ __device__ __noinline__ void tp_gather_x(float* xres, const float* src, int npar
 // the partial sums every rank pushed into this rank's arena (src + q * part_stride), added in rank order so
 // that all ranks hold bit-identical x. This is the receiving half of the fused all-reduce (forward.c:295-298,
 // 335-338 are the residual adds it replaces).
+template <bool TP>
 __device__ __forceinline__ void prologue_quant(const Shared& sh, const MegaParams& p, const float* src, int n, const float* __restrict__ nw, int nparts) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int groups = n / 64, recs = qw_sg_per_row(n);
@@ -640,7 +642,7 @@ __device__ __forceinline__ void prologue_quant(const Shared& sh, const MegaParam
             const int rec = r0 + k * kConsumerWarps;
             live[k] = rec < recs && rec * 4 + (lane >> 3) < groups;
         }
-        if (nparts < 0) {
+        if (!TP || nparts < 0) {
             uint4 a[kRecBatch], b[kRecBatch];
 #pragma unroll
             for (int k = 0; k < kRecBatch; ++k) {
@@ -1082,7 +1084,7 @@ __device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams&
 }
 
 // ---------------------------------------------------------------- consumer main
-template <int KV_MUL>
+template <int KV_MUL, bool TP>
 __device__ void consumer(const Shared& sh, const MegaParams& p) {
     // refill the OTHER arena with the sentinel for the next launch (nobody reads it during this one)
     {
@@ -1095,7 +1097,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
     }
     // the residual stream starts as the dequantised embedding row (forward.c:237): every CTA
     // contributes its slice of it to the flow vector x0
-    const bool tp = p.tp > 1;
+    constexpr bool tp = TP; // a separate instantiation: the single-GPU kernel carries no tensor-parallel code (instruction cache)
     const int tok = p.token_dev ? *p.token_dev : p.token;
     if (!tp) {
         const uint8_t* row = p.w_emb + (size_t) tok * qw_row_bytes(p.D);
@@ -1164,17 +1166,17 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
                 src = xprev; nw = p.out_norm; out = p.logits;
                 if (tp) nparts = xprev ? p.tp : 0;
             }
-            prologue_quant(sh, p, src, n, nw, nparts);
+            prologue_quant<TP>(sh, p, src, n, nw, nparts);
         }
         stamp(p, lp, 4 * (k & 3) + 2);
-        consume_mat(sh, p, p.mat[k], l, it, out, resid);
+        consume_mat<TP>(sh, p, p.mat[k], l, it, out, resid);
         stamp(p, lp, 4 * (k & 3) + 3);
         if (k == 3) xprev = fl + p.o_xb;
     }
 }
 
 // one instantiation per GQA ratio: only the attention code of the model at hand is in the kernel
-template <int KV_MUL>
+template <int KV_MUL, bool TP>
 __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int abort_flag;
@@ -1201,7 +1203,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ 
         if (threadIdx.x == kConsumerThreads) producer(sh, p);
         return;
     }
-    consumer<KV_MUL>(sh, p);
+    consumer<KV_MUL, TP>(sh, p);
 }
 
 // test hook: the decode kernel's own quantiser (quant_record: reciprocal candidate + exact fallback) over a
@@ -1224,12 +1226,12 @@ __global__ void k_fill_u32(uint32_t* dst, size_t n, uint32_t v) {
 
 // ---------------------------------------------------------------- host side
 static MegaState* state_of(QwenCudaCtx* c) { return reinterpret_cast<MegaState*>(c->mega); }
-static const void* decode_kernel(int kv_mul) {
+static const void* decode_kernel(int kv_mul, bool tp) {
     switch (kv_mul) {
-        case 1: return (const void*) k_decode<1>;
-        case 2: return (const void*) k_decode<2>;
-        case 4: return (const void*) k_decode<4>;
-        default: return (const void*) k_decode<8>;
+        case 1: return tp ? (const void*) k_decode<1, true> : (const void*) k_decode<1, false>;
+        case 2: return tp ? (const void*) k_decode<2, true> : (const void*) k_decode<2, false>;
+        case 4: return tp ? (const void*) k_decode<4, true> : (const void*) k_decode<4, false>;
+        default: return tp ? (const void*) k_decode<8, true> : (const void*) k_decode<8, false>;
     }
 }
 
@@ -1298,9 +1300,9 @@ int qw_mega_init(QwenCudaCtx* c) {
     st->off_bar = take(bar_b);
     st->off_xres = take(xres_b);
     st->smem = off;
-    QW_CUDA(cudaFuncSetAttribute(decode_kernel(kv_mul), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
+    QW_CUDA(cudaFuncSetAttribute(decode_kernel(kv_mul, c->tp_size > 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
     int per_sm = 0;
-    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel(kv_mul), kThreads, st->smem));
+    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel(kv_mul, c->tp_size > 1), kThreads, st->smem));
     if (per_sm < 1) {
         qw_set_error("persistent decode kernel does not fit on an SM (smem %zu)", st->smem);
         return -1;
@@ -1478,7 +1480,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.off_misc = st->off_misc; p.off_bar = st->off_bar;
     void* args[] = {&p};
     // cooperative launch: the CTAs wait for each other's results, so all of them must be resident
-    QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
+    QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul, c->tp_size > 1), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
     st->last_layers = p.layers_run;
     ++st->launches;
     // the classifier is split over vocabulary rows: gather the logits slices

@@ -380,7 +380,8 @@ def test_tensor_parallel_2gpu_matches_single_gpu(qlib, pkg, ckpt_dir):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    paths = [pkg.checkpoint.ensure_checkpoint(ckpt_dir, "small", seed=11), pkg.checkpoint.ensure_checkpoint(ckpt_dir, "8b-l2", seed=11)]
+    # small: 2 kv heads per rank; 8b-l2: the real 8B layer shape; tiny: ONE kv head per rank (what TP=8 looks like on 8 kv heads)
+    paths = [pkg.checkpoint.ensure_checkpoint(ckpt_dir, name, seed=11) for name in ("small", "8b-l2", "tiny")]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29531",
