@@ -177,6 +177,14 @@ __device__ __forceinline__ uint4 ldf_sys_u4(const void* p) {
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
+// "push my stores out now": see consume_mat. QW_FENCE=1 tries the lighter acq_rel fence instead of __threadfence()'s sc fence.
+__device__ __forceinline__ void flush_stores() {
+#if defined(QW_FENCE) && QW_FENCE == 1
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
+    __threadfence();
+#endif
+}
 __device__ __forceinline__ bool unset4(const uint4& v) { return v.x == kSent || v.y == kSent || v.z == kSent || v.w == kSent; }
 
 struct Shared {
@@ -259,6 +267,19 @@ __device__ __forceinline__ float4 as_f4(const uint4& v) {
     return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
 }
 __device__ __forceinline__ float* flow_layer(const MegaParams& p, int l) { return p.flow + (size_t) l * p.flow_layer_words; }
+
+// Position in the shared-memory ring: slot index and the mbarrier phase parity of this pass over the ring. Advanced by
+// one per tile; computing it as it % nslot, (it / nslot) & 1 put a runtime integer division (I2F + MUFU.RCP + fix-up,
+// ~40 dependent instructions) into every tile iteration of every warp: 5 % of all stall samples in ncu.
+struct RingPos {
+    unsigned slot, par;
+    __device__ __forceinline__ void next(int nslot) {
+        if (++slot == (unsigned) nslot) {
+            slot = 0;
+            par ^= 1u;
+        }
+    }
+};
 
 // ---------------------------------------------------------------- schedule (shared by producer and consumers)
 // The step is a fixed list of phases: 4 per layer (QKV, WO, W1/W3, W2) and the classifier. Producer and
@@ -351,7 +372,7 @@ __device__ __noinline__ void prefetch_subphase(const MegaParams& p, int sp) {
 // 28 KB in flight top out at 7.5 TB/s either way -- so the ring refills no sooner and the step time does
 // not improve (2.07 ms vs 2.14 ms with the prefetch on).
 __device__ void producer(const Shared& sh, const MegaParams& p) {
-    unsigned it = 0;
+    RingPos rp{0u, 0u};
     const int nph = 4 * p.layers_run;
     int sp = 0;
 #pragma unroll 1
@@ -362,9 +383,9 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
             ++sp;
             const AttnSplit a = attn_split(p);
 #pragma unroll 1
-            for (int p0 = a.p_lo; p0 < a.p_hi; p0 += kChunk, ++it) {
+            for (int p0 = a.p_lo; p0 < a.p_hi; p0 += kChunk, rp.next(p.nslot)) {
                 const int cnt = min(kChunk, a.p_hi - p0);
-                const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
+                const unsigned slot = rp.slot, par = rp.par;
                 mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 2);
                 const size_t off = (((size_t) l * p.KVHl + a.kvh) * p.S + p0) * 128;
                 const uint32_t bytes = (uint32_t) cnt * 512u;
@@ -382,9 +403,9 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
         const size_t rb = qw_row_bytes(m.n);
         const uint8_t* base = m.base + (size_t) l * m.stride;
 #pragma unroll 1
-        for (int r = r0; r < r1; r += m.rt, ++it) {
+        for (int r = r0; r < r1; r += m.rt, rp.next(p.nslot)) {
             const int nr = min(m.rt, r1 - r);
-            const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
+            const unsigned slot = rp.slot, par = rp.par;
             mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 1);
             const uint32_t bytes = (uint32_t) (nr * rb);
             mbar_expect_tx(sh.full + slot * 8, bytes);
@@ -411,7 +432,7 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
 // own rank is one of the q). That IS the all-reduce: the readers add the tp slots in rank order (prologue_quant).
 // `out` is a flow-arena vector (or the logits): each element is stored exactly once.
 template <bool TP>
-__device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& p, const MatDesc& m, int /*layer*/, unsigned& it, float* out, const float* resid) {
+__device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& p, const MatDesc& m, int /*layer*/, RingPos& rp, float* out, const float* resid) {
     int r0, r1;
     cta_rows(m, p.perm, r0, r1);
     const int rt = m.rt;
@@ -425,17 +446,18 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     const int upt = (rt + 1) / 2;             // units per tile (rt is 1 only when a row fills the slot)
     const int rows_pu = rt >= 2 ? 2 : 1;      // rows per unit
     const int total = (nrows + rows_pu - 1) / rows_pu;
+    int u = warp; // this warp's next unit
 #pragma unroll 1
-    for (int t0 = 0; t0 < total; t0 += upt, ++it) {
-        const unsigned slot = it % p.nslot, par = (it / p.nslot) & 1;
+    for (int t0 = 0; t0 < total; t0 += upt, rp.next(p.nslot)) {
+        const unsigned slot = rp.slot, par = rp.par;
         mbar_wait(sh, p, sh.full + slot * 8, par, 3);
         const uint8_t* tile = sh.ring + (size_t) slot * kSlotBytes;
-        const int t1 = p.dbg_mode >= 1 ? t0 : min(t0 + upt, total);
+        const int t1 = min(t0 + upt, total);
         bool released = false;
-        int ufirst = (warp - t0) % kConsumerWarps; // first unit >= t0 owned by this warp (u % 15 == warp)
-        if (ufirst < 0) ufirst += kConsumerWarps;
+        if (p.dbg_mode >= 1) // ring throughput test: skip the math
+            while (u < t1) u += kConsumerWarps;
 #pragma unroll 1
-        for (int u = t0 + ufirst; u < t1; u += kConsumerWarps) {
+        for (; u < t1; u += kConsumerWarps) { // this warp's units u = warp, warp + 15, ... fall into the tiles in order
             const int lr = (u - t0) * rows_pu;          // first row of the unit inside the tile
             const int grow = r0 + u * rows_pu;          // its global row
             const bool two = rows_pu == 2 && grow + 1 < r1;
@@ -511,7 +533,7 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     }
     // push this warp's results out NOW: without a fence the stores sit in the SM's write path for
     // microseconds (measured, scripts/ubench/handoff.cu: 2.7 us per hand-off without, 1.05 us with)
-    if (TP && KIND == 3) __threadfence_system(); else __threadfence();
+    if (TP && KIND == 3) __threadfence_system(); else flush_stores();
 }
 
 // ---------------------------------------------------------------- consumer: prologues
@@ -798,7 +820,7 @@ constexpr int kScrFloats = 8 * 4 * kPartStride;
 // equal contiguous ranges (a range may straddle two tiles), so the load is balanced at any context
 // length. Every warp walks every tile for the ring protocol.
 template <int KV_MUL>
-__device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsigned& it) {
+__device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, RingPos& rp) {
     constexpr int HW = KV_MUL < 4 ? KV_MUL : 4; // heads per warp
     constexpr int NHG = KV_MUL / HW;            // head groups per KV head
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -807,7 +829,6 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
     const float* qkv = fl + p.o_qkv;
     const float* gq = p.q_norm + (size_t) l * 128;
     const float* gk = p.k_norm + (size_t) l * 128;
-    const unsigned it_base = it;
     const AttnSplit as = attn_split(p);
     if (!as.active) return; // this block has no share of the attention (no tiles, no partial expected from it)
     const int kvh = as.kvh, my_slot = as.j;
@@ -824,7 +845,7 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
             float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + my_slot) * KV_MUL + lane) * kPartStride;
             stf_f32(dst + 128, -INFINITY);
             stf_f32(dst + 129, 0.0f);
-            __threadfence();
+            flush_stores();
         }
         return;
     }
@@ -871,23 +892,24 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
             const int my0 = gn * wi / wn, my1 = gn * (wi + 1) / wn;           // this warp's, relative to the group
             const float* Ka = nullptr;
             int cnta = 0;
+            unsigned prev_slot = 0;
 #pragma unroll 1
-            for (int t = 0; t < gt; ++t) {
-                const unsigned itx = it_base + (unsigned) (g0 + t);
-                const unsigned slot = itx % p.nslot;
-                mbar_wait(sh, p, sh.full + slot * 8, (itx / p.nslot) & 1, 4);
+            for (int t = 0; t < gt; ++t, rp.next(p.nslot)) { // every warp walks every tile, in order
+                const unsigned slot = rp.slot;
+                mbar_wait(sh, p, sh.full + slot * 8, rp.par, 4);
                 const int a = max(my0, t * kChunk) - t * kChunk, b = min(my1, (t + 1) * kChunk) - t * kChunk;
                 const float* Kt = reinterpret_cast<const float*>(sh.ring + (size_t) slot * kSlotBytes) + a * 128;
                 const bool more = my1 > (t + 1) * kChunk && t + 1 < gt; // my range continues in the next tile
                 if (b > a && more) { // first of two tiles: remember it, its slot is released below
                     Ka = Kt;
                     cnta = b - a;
+                    prev_slot = slot;
                     continue;
                 }
                 if (b > a) attn_rows<HW>(Ka ? Ka : Kt, Ka ? cnta : b - a, Kt, (Ka ? cnta : 0) + b - a, kChunk * 128, q, st, lane);
                 __syncwarp();
                 if (lane == 0) {
-                    if (Ka) mbar_arrive(sh.empty + ((itx - 1) % p.nslot) * 8);
+                    if (Ka) mbar_arrive(sh.empty + prev_slot * 8);
                     mbar_arrive(sh.empty + slot * 8);
                 }
                 Ka = nullptr;
@@ -916,10 +938,9 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, unsig
                     stf_f32(dst + j * kPartStride + 129, st.l[j]);
                 }
             }
-            __threadfence(); // flush (see consume_mat)
+            flush_stores(); // flush (see consume_mat)
         }
     }
-    it = it_base + (unsigned) ntile;
 }
 
 // Combine (CTA-wide): task t = (head h, half hf) merges the published partials of the head (online-
@@ -1078,7 +1099,7 @@ __device__ __forceinline__ void combine_attn(const Shared& sh, const MegaParams&
                 stf_u32(rec + (g & 3) * 64 + 32 + lane, w1);
             }
             if (lane == 0) stf_f32(reinterpret_cast<float*>(rec + 256 + (g & 3) * 4), scale);
-            __threadfence(); // flush (see consume_mat)
+            flush_stores(); // flush (see consume_mat)
         }
     }
 }
@@ -1108,7 +1129,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
             const float sc = *reinterpret_cast<const float*>(rec + 256 + ((c >> 6) & 3) * 4);
             stf_f32(p.flow_x0 + c, __fmul_rn((float) reinterpret_cast<const int8_t*>(rec)[c & 255], sc));
         }
-        __threadfence();
+        flush_stores();
     } else {
         // tensor parallel: every CTA keeps the whole residual stream in shared memory; each thread dequantises the
         // elements it owns in prologue_quant (records warp, warp + 15, warp + 30; 8 columns per lane)
@@ -1129,7 +1150,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
             }
         }
     }
-    unsigned it = 0;
+    RingPos rp{0u, 0u};
     const float* xprev = p.flow_x0; // residual stream entering the layer (tp: the last w2's per-rank partials, or null)
     if (tp) xprev = nullptr;
     const int nph = 4 * p.layers_run;
@@ -1142,7 +1163,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
         const float* resid = nullptr;
         stamp(p, lp, 4 * (k & 3));
         if (k == 1) { // attention block, second half (forward.c:261-298)
-            consume_attn<KV_MUL>(sh, p, l, it);
+            consume_attn<KV_MUL>(sh, p, l, rp);
             stamp(p, lp, 13);
             combine_attn(sh, p, l);
             stamp(p, lp, 5);
@@ -1169,7 +1190,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
             prologue_quant<TP>(sh, p, src, n, nw, nparts);
         }
         stamp(p, lp, 4 * (k & 3) + 2);
-        consume_mat<TP>(sh, p, p.mat[k], l, it, out, resid);
+        consume_mat<TP>(sh, p, p.mat[k], l, rp, out, resid);
         stamp(p, lp, 4 * (k & 3) + 3);
         if (k == 3) xprev = fl + p.o_xb;
     }
