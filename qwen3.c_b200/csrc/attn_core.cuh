@@ -102,3 +102,30 @@ __device__ __forceinline__ void attn_rows(const float* Ka, int cnta, const float
     }
 }
 
+
+// ONE position (K row k, V row v: this lane's 4 dims of each) for HW query heads, without the 8-position block
+// machinery of attn_rows: the decode step's own position, which would otherwise cost a whole block of masked work on
+// the critical path of the blocks every combine task waits for. Same operations per head as attn_rows (the xor tree
+// adds the 32 lane partials in the same pairing as the butterfly).
+template <int HW>
+__device__ __forceinline__ void attn_one_row(const float4 kf, const float4 vv, const float4 (&q)[HW], AttnState<HW>& st) {
+    const float inv = sqrtf(128.0f);
+#pragma unroll
+    for (int j = 0; j < HW; ++j) {
+        float d = __fmul_rn(q[j].x, kf.x);
+        d = __fmaf_rn(q[j].y, kf.y, d);
+        d = __fmaf_rn(q[j].z, kf.z, d);
+        d = __fmaf_rn(q[j].w, kf.w, d);
+        d = warp_sum(d);
+        const float sc = __fdiv_rn(d, inv);
+        const float m_new = fmaxf(st.m[j], sc);
+        const float scl = (st.m[j] == -INFINITY) ? 0.0f : expf(__fsub_rn(st.m[j], m_new));
+        const float e = expf(__fsub_rn(sc, m_new));
+        st.m[j] = m_new;
+        st.l[j] = __fadd_rn(__fmul_rn(st.l[j], scl), e);
+        st.acc[j].x = __fmaf_rn(e, vv.x, __fmul_rn(st.acc[j].x, scl));
+        st.acc[j].y = __fmaf_rn(e, vv.y, __fmul_rn(st.acc[j].y, scl));
+        st.acc[j].z = __fmaf_rn(e, vv.z, __fmul_rn(st.acc[j].z, scl));
+        st.acc[j].w = __fmaf_rn(e, vv.w, __fmul_rn(st.acc[j].w, scl));
+    }
+}

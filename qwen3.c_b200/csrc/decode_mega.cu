@@ -65,6 +65,7 @@ struct MatDesc {
     size_t stride;       // bytes between layers
     int rows, n, gran;   // rows, columns, granularity of the per-CTA row split
     int rt;              // rows per ring tile
+    int stage;           // 1: results are collected in shared memory and leave as ONE bulk store per CTA (see consume_mat)
     int kind;            // epilogue: 0 out[row] = v, 1 out[row] = resid[row] + v, 2 out[row/2] = silu(v0) * v1,
                          // 3 tensor parallel: this rank's partial v goes to slot tp_rank of EVERY rank's arena (peer stores)
 };
@@ -218,6 +219,18 @@ __device__ __noinline__ void mbar_wait_slow(volatile int* abort_flag, int* err, 
 __device__ __forceinline__ void mbar_wait(const Shared& sh, const MegaParams& p, uint32_t bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return;
     mbar_wait_slow(sh.abort_flag, p.err, bar, parity, code);
+}
+// shared tail of the inline polling loops: called every 256 rounds; true = give up (abort raised here or elsewhere)
+__device__ __noinline__ bool poll_timed_out(volatile int* abort_flag, int* err, unsigned long long& t0, int code) {
+    if (*abort_flag) return true;
+    const unsigned long long now = gtime_ns();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > kTimeoutNs) {
+        *abort_flag = code;
+        *err = code;
+        return true;
+    }
+    return false;
 }
 // poll until the 4 (or 1) words at q are all written
 __device__ __noinline__ uint4 poll4_slow(volatile int* abort_flag, int* err, const void* q, int code) {
@@ -446,6 +459,8 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     const int upt = (rt + 1) / 2;             // units per tile (rt is 1 only when a row fills the slot)
     const int rows_pu = rt >= 2 ? 2 : 1;      // rows per unit
     const int total = (nrows + rows_pu - 1) / rows_pu;
+    const bool staged = m.stage != 0;
+    float* stage = sh.scr;                    // free during the GEMV phases (attention / combine scratch)
     int u = warp; // this warp's next unit
 #pragma unroll 1
     for (int t0 = 0; t0 < total; t0 += upt, rp.next(p.nslot)) {
@@ -512,7 +527,10 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
                 accb = __fadd_rn(accb, __shfl_xor_sync(0xffffffffu, accb, o));
             }
             if (KIND == 2) {
-                if (lane == 0) stf_f32(out + (grow >> 1), __fmul_rn(silu_ref(acca), accb));
+                if (lane == 0) {
+                    const float hv = __fmul_rn(silu_ref(acca), accb);
+                    if (staged) stage[(grow - r0) >> 1] = hv; else stf_f32(out + (grow >> 1), hv);
+                }
             } else if (TP && KIND == 3) {
                 if (lane < 2 * p.tp && ((lane & 1) == 0 || two)) {
                     char* base = reinterpret_cast<char*>(p.peer_flow[0]);
@@ -523,7 +541,8 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
                 }
             } else if (lane < 2 && (lane == 0 || two)) {
                 const float v = lane == 0 ? acca : accb;
-                stf_f32(out + grow + lane, KIND == 1 ? __fadd_rn(xres, v) : v);
+                const float o = KIND == 1 ? __fadd_rn(xres, v) : v;
+                if (staged) stage[grow + lane - r0] = o; else stf_f32(out + grow + lane, o);
             }
         }
         if (!released) { // no unit of this warp in the tile
@@ -533,7 +552,24 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     }
     // push this warp's results out NOW: without a fence the stores sit in the SM's write path for
     // microseconds (measured, scripts/ubench/handoff.cu: 2.7 us per hand-off without, 1.05 us with)
-    if (TP && KIND == 3) __threadfence_system(); else flush_stores();
+    if (staged) {
+        // The CTA's rows are contiguous in the output vector: once every warp has put its results into shared memory, one
+        // thread sends them with a single TMA bulk store. The async proxy writes straight to L2 -- no SM store queue shared
+        // with the polling loads, and no warp waits in a fence (13 % of all stall samples in ncu with per-warp stores + fence).
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bar_consumers();
+        if (threadIdx.x == 0 && nrows > 0) {
+            const int nout = KIND == 2 ? nrows >> 1 : nrows;
+            float* dst = out + (KIND == 2 ? r0 >> 1 : r0);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stage)), "r"(nout * 4) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the staging area may be rewritten after the next CTA barrier
+        }
+    } else if (TP && KIND == 3) {
+        __threadfence_system();
+    } else {
+        flush_stores();
+    }
 }
 
 // ---------------------------------------------------------------- consumer: prologues
@@ -674,14 +710,32 @@ __device__ __forceinline__ void prologue_quant(const Shared& sh, const MegaParam
                     b[k] = ldf_u4(src + rec * 256 + lane * 8 + 4);
                 }
             }
+            // poll: re-issue ALL still-unset pieces together each round (one L2 round trip per round). Polling them one
+            // after the other cost up to six serial round trips after the data had landed, because every piece's first
+            // load was issued before its producer had stored.
+            {
+                unsigned long long t_start = 0;
+#pragma unroll 1
+                for (unsigned n = 1;; ++n) {
+                    bool busy = false;
+#pragma unroll
+                    for (int k = 0; k < kRecBatch; ++k)
+                        if (live[k]) busy |= unset4(a[k]) | unset4(b[k]);
+                    if (!busy) break;
+                    if ((n & 255u) == 0 && poll_timed_out(sh.abort_flag, p.err, t_start, 10)) break;
+#pragma unroll
+                    for (int k = 0; k < kRecBatch; ++k) {
+                        const float* q = src + (r0 + k * kConsumerWarps) * 256 + lane * 8;
+                        if (live[k] && unset4(a[k])) a[k] = ldf_u4(q);
+                        if (live[k] && unset4(b[k])) b[k] = ldf_u4(q + 4);
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < kRecBatch; ++k) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[k][i] = 0.0f;
                 if (live[k]) {
-                    const float* q = src + (r0 + k * kConsumerWarps) * 256 + lane * 8;
-                    if (unset4(a[k])) a[k] = poll4_slow(sh.abort_flag, p.err, q, 10);
-                    if (unset4(b[k])) b[k] = poll4_slow(sh.abort_flag, p.err, q + 4, 10);
                     v[k][0] = __uint_as_float(a[k].x); v[k][1] = __uint_as_float(a[k].y);
                     v[k][2] = __uint_as_float(a[k].z); v[k][3] = __uint_as_float(a[k].w);
                     v[k][4] = __uint_as_float(b[k].x); v[k][5] = __uint_as_float(b[k].y);
@@ -859,9 +913,20 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, RingP
             float x[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) x[k] = __uint_as_float(ldf_u32(src + lane + 32 * k));
+            {
+                unsigned long long t_start = 0;
+#pragma unroll 1
+                for (unsigned n = 1;; ++n) { // all four words re-polled together (see prologue_quant)
+                    bool busy = false;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (__float_as_uint(x[k]) == kSent) x[k] = poll1(sh, p, src + lane + 32 * k, 13);
+                    for (int k = 0; k < 4; ++k) busy |= __float_as_uint(x[k]) == kSent;
+                    if (!busy) break;
+                    if ((n & 255u) == 0 && poll_timed_out(sh.abort_flag, p.err, t_start, 13)) break;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (__float_as_uint(x[k]) == kSent) x[k] = __uint_as_float(ldf_u32(src + lane + 32 * k));
+                }
+            }
             float* dst = sq + warp * 128;
             if (warp <= KV_MUL) {
                 head_norm_rope_warp(dst, x, warp < KV_MUL ? gq : gk, p, lane);
@@ -916,7 +981,9 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, RingP
             }
         }
         // this step's own position, from shared memory: the last warp of each head group takes it
-        if (own_last && wi == wn - 1) attn_rows<HW>(sq + KV_MUL * 128, 1, sq + KV_MUL * 128, 1, 128, q, st, lane);
+        if (own_last && wi == wn - 1)
+            attn_one_row<HW>(*reinterpret_cast<const float4*>(sq + KV_MUL * 128 + lane * 4),
+                             *reinterpret_cast<const float4*>(sq + (KV_MUL + 1) * 128 + lane * 4), q, st);
         // ---- merge the warp states pairwise through shared memory (w <- w + half keeps w % NHG)
         bar_consumers(); // sq is dead from here
         stamp(p, l, 9);
@@ -927,18 +994,28 @@ __device__ void consume_attn(const Shared& sh, const MegaParams& p, int l, RingP
             if (warp < half && warp + half < kConsumerWarps) attn_merge_in<HW>(st, sh.scr + warp * (HW * kPartStride), lane);
             bar_consumers();
         }
-        // ---- publish (m, l, acc) of this CTA for the segment's heads
+        // ---- publish (m, l, acc) of this CTA for the segment's heads: the KV_MUL x 132 floats are contiguous in the arena,
+        // so they are assembled in shared memory and leave as one TMA bulk store (no per-warp fence; see consume_mat)
         if (warp < NHG) {
-            float* dst = fl + p.o_part + ((size_t) (kvh * p.part_slots + my_slot) * KV_MUL + warp * HW) * kPartStride;
+            float* dst = sh.scr + (warp * HW) * kPartStride;
 #pragma unroll
             for (int j = 0; j < HW; ++j) {
-                stf_f4(dst + j * kPartStride + lane * 4, st.acc[j]);
+                *reinterpret_cast<float4*>(dst + j * kPartStride + lane * 4) = st.acc[j];
                 if (lane == 0) {
-                    stf_f32(dst + j * kPartStride + 128, st.m[j]);
-                    stf_f32(dst + j * kPartStride + 129, st.l[j]);
+                    dst[j * kPartStride + 128] = st.m[j];
+                    dst[j * kPartStride + 129] = st.l[j];
+                    dst[j * kPartStride + 130] = 0.0f; // pad words: never read
+                    dst[j * kPartStride + 131] = 0.0f;
                 }
             }
-            flush_stores(); // flush (see consume_mat)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        bar_consumers();
+        if (threadIdx.x == 0) {
+            float* gdst = fl + p.o_part + ((size_t) (kvh * p.part_slots + my_slot) * KV_MUL) * kPartStride;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(sh.scr)), "r"(KV_MUL * kPartStride * 4) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // combine_attn reuses the scratch after its barrier
         }
     }
 }
@@ -1469,18 +1546,25 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.S = c->S; p.kv_mul = c->Hl / c->KVHl;
     p.pos = pos; p.token = token; p.token_dev = token_dev;
     p.layers_run = (c->layers_run >= 0 && c->layers_run <= c->L) ? c->layers_run : c->L;
-    auto desc = [](const uint8_t* base, size_t stride, int rows, int n, int gran, int kind) {
+    int stage_env = 1; // QWEN_MEGA_STAGE=0: per-warp stores + fence instead of the staged bulk store
+    if (const char* e = getenv("QWEN_MEGA_STAGE")) stage_env = atoi(e);
+    const int grid = st->grid;
+    auto desc = [stage_env, grid](const uint8_t* base, size_t stride, int rows, int n, int kind) {
         int rt = kSlotBytes / (int) qw_row_bytes(n);
         if (rt >= 2) rt &= ~1; // whole 2-row units per tile
-        if (rt < gran) rt = gran;
-        return MatDesc{base, stride, rows, n, gran, rt, kind};
+        if (rt < 2 && kind == 2) rt = 2;
+        // staged bulk store: a CTA's slice of the output must start and end on 16 bytes (4 rows; 8 for the w1/w3 pairs)
+        const int sg = kind == 2 ? 8 : 4;
+        const bool stage = stage_env && kind != 3 && rows % sg == 0 && (rows / sg / grid + 1) * sg <= kScrFloats;
+        const int gran = stage ? sg : (kind == 2 ? 2 : 1);
+        return MatDesc{base, stride, rows, n, gran, rt, stage ? 1 : 0, kind};
     };
-    p.mat[0] = desc(c->w_qkv, c->w_qkv_stride, c->Pl + 2 * c->Kl, c->D, 1, 0);
+    p.mat[0] = desc(c->w_qkv, c->w_qkv_stride, c->Pl + 2 * c->Kl, c->D, 0);
     const int kres = c->tp_size > 1 ? 3 : 1; // wo / w2 epilogue: residual add on one GPU, partial push under tensor parallelism
-    p.mat[1] = desc(c->w_o, c->w_o_stride, c->D, c->Pl, 1, kres);
-    p.mat[2] = desc(c->w_13, c->w_13_stride, 2 * c->Hdl, c->D, 2, 2);
-    p.mat[3] = desc(c->w_2, c->w_2_stride, c->D, c->Hdl, 1, kres);
-    p.mat[4] = desc(c->w_cls, 0, c->Vl, c->D, 1, 0);
+    p.mat[1] = desc(c->w_o, c->w_o_stride, c->D, c->Pl, kres);
+    p.mat[2] = desc(c->w_13, c->w_13_stride, 2 * c->Hdl, c->D, 2);
+    p.mat[3] = desc(c->w_2, c->w_2_stride, c->D, c->Hdl, kres);
+    p.mat[4] = desc(c->w_cls, 0, c->Vl, c->D, 0);
     p.w_emb = c->w_emb;
     p.att_norm = c->att_norm; p.ffn_norm = c->ffn_norm; p.out_norm = c->out_norm; p.q_norm = c->q_norm; p.k_norm = c->k_norm;
     p.rope_cos = c->rope_cos; p.rope_sin = c->rope_sin;
