@@ -531,6 +531,8 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
                     const float hv = __fmul_rn(silu_ref(acca), accb);
                     if (staged) stage[(grow - r0) >> 1] = hv; else stf_f32(out + (grow >> 1), hv);
                 }
+            } else if (TP && KIND == 3 && staged) {
+                if (lane < 2 && (lane == 0 || two)) stage[grow + lane - r0] = lane == 0 ? acca : accb;
             } else if (TP && KIND == 3) {
                 if (lane < 2 * p.tp && ((lane & 1) == 0 || two)) {
                     char* base = reinterpret_cast<char*>(p.peer_flow[0]);
@@ -558,7 +560,20 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
         // with the polling loads, and no warp waits in a fence (13 % of all stall samples in ncu with per-warp stores + fence).
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         bar_consumers();
-        if (threadIdx.x == 0 && nrows > 0) {
+        if (TP && KIND == 3) {
+            // tensor parallel: one bulk store per rank, issued by threads 0 .. tp-1, straight into slot tp_rank of that
+            // rank's arena over NVLink (`out` is the byte offset of the slot) -- the sending half of the fused all-reduce
+            if ((int) threadIdx.x < p.tp && nrows > 0) {
+                char* base = reinterpret_cast<char*>(p.peer_flow[0]);
+#pragma unroll
+                for (int q = 1; q < kMaxTp; ++q) // static indices: a dynamic one makes a local copy of the parameter array
+                    if ((int) threadIdx.x == q) base = reinterpret_cast<char*>(p.peer_flow[q]);
+                float* dst = reinterpret_cast<float*>(base + reinterpret_cast<size_t>(out)) + r0;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stage)), "r"(nrows * 4) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else if (threadIdx.x == 0 && nrows > 0) {
             const int nout = KIND == 2 ? nrows >> 1 : nrows;
             float* dst = out + (KIND == 2 ? r0 >> 1 : r0);
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stage)), "r"(nout * 4) : "memory");
@@ -1192,6 +1207,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
         const uint4 s4 = make_uint4(kSent, kSent, kSent, kSent);
 #pragma unroll 1
         for (unsigned i = a + threadIdx.x; i < b; i += kConsumerThreads) dst[i] = s4;
+        if (TP) __threadfence_system(); // peers write into that arena during the next launch: the refill must be ahead of them
     }
     // the residual stream starts as the dequantised embedding row (forward.c:237): every CTA
     // contributes its slice of it to the flow vector x0
@@ -1555,7 +1571,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         if (rt < 2 && kind == 2) rt = 2;
         // staged bulk store: a CTA's slice of the output must start and end on 16 bytes (4 rows; 8 for the w1/w3 pairs)
         const int sg = kind == 2 ? 8 : 4;
-        const bool stage = stage_env && kind != 3 && rows % sg == 0 && (rows / sg / grid + 1) * sg <= kScrFloats;
+        const bool stage = stage_env && rows % sg == 0 && (rows / sg / grid + 1) * sg <= kScrFloats;
         const int gran = stage ? sg : (kind == 2 ? 2 : 1);
         return MatDesc{base, stride, rows, n, gran, rt, stage ? 1 : 0, kind};
     };

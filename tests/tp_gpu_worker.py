@@ -30,18 +30,20 @@ def one_checkpoint(pkg, ql, orc, path, rank, world, n_tokens, require_peer):
         ref = [om.forward(int(t), pos) for pos, t in enumerate(toks)]
         ref_chain, tok = [], 17  # the oracle's own greedy continuation: (token, top-2 margin) per step
         for i in range(16):
-            nxt, margin = orc.argmax(om.forward(tok, n_tokens + i))
-            ref_chain.append((int(nxt), float(margin)))
+            lo = om.forward(tok, n_tokens + i)
+            nxt, margin = orc.argmax(lo)
+            ref_chain.append((int(nxt), float(margin), float(lo.std())))
             tok = int(nxt)
     per_path = {}
     for sel in ([0, 1] if fused else [1]):
         gm.set_path(sel)
-        outs = []
+        outs, eps = [], 0.0
         for pos, t in enumerate(toks):
             lg, lo = gm.forward(int(t), pos), ref[pos]
             assert int(lg.argmax()) == int(lo.argmax()), (rank, sel, pos)
             assert np.abs(lg - lo).max() <= 0.05 * max(1.0, lo.std()), (rank, sel, pos, float(np.abs(lg - lo).max()))
             outs.append(lg.copy())
+            eps = max(eps, float(np.abs(lg - lo).max()))
         if sel == 0:  # the fused path is deterministic: the same step again (same cache below it) gives the same bits
             again = gm.forward(int(toks[-1]), n_tokens - 1)
             assert np.array_equal(again.view(np.uint32), outs[-1].view(np.uint32))
@@ -50,9 +52,11 @@ def one_checkpoint(pkg, ql, orc, path, rank, world, n_tokens, require_peer):
         r0 = t.clone()
         dist.broadcast(r0, src=0)
         assert torch.equal(t, r0), "ranks disagree on the greedy chain"
-        for i, (nxt, margin) in enumerate(ref_chain):  # follows the oracle until a step whose top-2 margin is inside the noise
+        # follows the oracle until a step whose top-2 margin is inside the accepted logit noise (each logit may move by
+        # 0.05 * std -- the bound asserted per step above, DESIGN.md 5 -- so two of them can swap when margin < 2 x that)
+        for i, (nxt, margin, std) in enumerate(ref_chain):
             if int(chain[i]) != nxt:
-                assert margin < 2e-2, (sel, i, int(chain[i]), nxt, margin)
+                assert margin < max(2e-2, 2.0 * eps, 0.1 * max(1.0, std)), (sel, i, int(chain[i]), nxt, margin, eps, std)
                 break
         # all ranks must hold bit-identical logits (the partials are added in rank order everywhere)
         lt = torch.tensor(np.stack(outs), device="cuda")
