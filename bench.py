@@ -224,6 +224,13 @@ def main():
                           "kernel": "k_decode (persistent, 1 launch/token)" if args.path == "mega" else "per-op kernels",
                           "frac_of_8TBs_nominal": achieved / 8000.0})
     line["config"]["path"] = args.path
+    try:  # dram bytes per launch of k_decode from the committed ncu capture of this workload (profiles/r1_traffic.json)
+        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+        if args.path == "mega" and workload in tr:
+            line["roofline"]["traffic"] = tr[workload]["traffic"]
+            line["roofline"]["traffic_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_traffic.json)"
+    except Exception:
+        pass
     # (3) prompt prefill on the same model (north_star: prefill tok/s + int8 tensor-pipe fraction): 512 tokens at
     # positions 0..511 through forward_prefill's device entry, host tokens in, no logits copy; best of 3
     try:
