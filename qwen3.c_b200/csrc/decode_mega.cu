@@ -665,20 +665,20 @@ __device__ __noinline__ void tp_gather_x(float* xres, const float* src, int npar
         const int col = rec * 256 + lane * 8;
         float4* xr = reinterpret_cast<float4*>(xres + col);
         float4 x0 = xr[0], x1 = xr[1];
-        {   // all ranks' partials in flight at once (one round trip; kMaxTp x 2 x 16 bytes per thread -- this function is
-            // out of line, so the registers are its own)
-            uint4 a[kMaxTp], b[kMaxTp];
+#pragma unroll 1
+        for (int q0 = 0; q0 < nparts; q0 += 4) { // four ranks' partials in flight at once
+            uint4 a[4], b[4];
 #pragma unroll
-            for (int j = 0; j < kMaxTp; ++j)
-                if (j < nparts) {
-                    const float* q = src + (size_t) j * part_stride + col;
+            for (int j = 0; j < 4; ++j)
+                if (q0 + j < nparts) {
+                    const float* q = src + (size_t) (q0 + j) * part_stride + col;
                     a[j] = ldf_sys_u4(q);
                     b[j] = ldf_sys_u4(q + 4);
                 }
 #pragma unroll
-            for (int j = 0; j < kMaxTp; ++j)
-                if (j < nparts) {
-                    const float* q = src + (size_t) j * part_stride + col;
+            for (int j = 0; j < 4; ++j)
+                if (q0 + j < nparts) {
+                    const float* q = src + (size_t) (q0 + j) * part_stride + col;
                     if (unset4(a[j])) a[j] = poll4_sys_slow(abort_flag, err, q, 15);
                     if (unset4(b[j])) b[j] = poll4_sys_slow(abort_flag, err, q + 4, 15);
                     x0.x = __fadd_rn(x0.x, __uint_as_float(a[j].x)); x0.y = __fadd_rn(x0.y, __uint_as_float(a[j].y));
