@@ -538,6 +538,28 @@ def test_persistent_kernel_is_deterministic(qlib, pkg, ckpt_dir):
         same(x, y)
 
 
+@pytest.mark.parametrize("shape_name", ["4b-l2", "tiny-untied"])
+def test_staged_bulk_store_publish_equals_per_warp_stores(qlib, pkg, ckpt_dir, shape_name, monkeypatch):
+    """The persistent kernel publishes each CTA's GEMV rows with one TMA bulk store from shared memory (row ranges in
+    units of 4 rows); QWEN_MEGA_STAGE=0 selects the older per-warp stores + fence with rows split to the row. Only the
+    way results travel differs, so the logits must be bit-identical, including across a context that switches modes
+    between steps (the variable is read per launch)."""
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, shape_name, seed=11)
+    V = pkg.checkpoint.SHAPES[shape_name].vocab_size
+    toks = [int(t) for t in np.random.default_rng(8).integers(0, V, size=10)]
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QWEN_MEGA_STAGE", mode)
+        with qlib.open(path, 32) as gm:
+            outs[mode] = [gm.forward(t, pos) for pos, t in enumerate(toks)]
+    for x, y in zip(outs["1"], outs["0"]):
+        same(x, y)
+    with qlib.open(path, 32) as gm:  # alternate per step
+        for pos, t in enumerate(toks):
+            monkeypatch.setenv("QWEN_MEGA_STAGE", str(pos & 1))
+            same(gm.forward(t, pos), outs["1"][pos])
+
+
 def test_4b_full_shape_first_tokens(qlib, oracle, pkg, ckpt_dir):
     """The headline configuration's checkpoint (Qwen3-4B shape, 36 layers, vocabulary 151936, fast-mode weights as in
     bench.py): the first decode steps of the persistent kernel and a 3-token forward_prefill against the oracle."""
