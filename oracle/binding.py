@@ -85,6 +85,13 @@ class Oracle:
         L.orc_trace_enable.argtypes = [C.POINTER(_OrcModel)]
         L.orc_argmax.restype = C.c_int
         L.orc_argmax.argtypes = [c_float_p, C.c_int, c_float_p]
+        L.orc_sample.restype = C.c_int
+        L.orc_sample.argtypes = [c_float_p, C.c_int, C.c_float, C.c_float, C.c_float, c_float_p]
+        L.orc_xorshift_float.restype = C.c_float
+        L.orc_xorshift_float.argtypes = [C.POINTER(C.c_uint64)]
+        L.orc_xorshift_int32.restype = C.c_uint32
+        L.orc_xorshift_int32.argtypes = [C.POINTER(C.c_uint64)]
+        L.orc_sampler_clamp.argtypes = [c_float_p, c_float_p]
         L.orc_sigmoid.restype = C.c_float
         L.orc_sigmoid.argtypes = [C.c_float]
         L.orc_silu.restype = C.c_float
@@ -145,6 +152,25 @@ class Oracle:
         m = C.c_float(0)
         i = self.lib.orc_argmax(_fp(v), C.c_int(v.size), C.byref(m))
         return i, m.value
+
+    # -- sampler (reference src/sampler.c, src/xorshift.c) ---------------
+    def sampler_clamp(self, temperature: float, top_p: float):
+        t, p = C.c_float(temperature), C.c_float(top_p)
+        self.lib.orc_sampler_clamp(C.byref(t), C.byref(p))
+        return t.value, p.value
+
+    def sample(self, logits, temperature: float, top_p: float, coin: float):
+        """sample() on a copy of `logits` with already clamped temperature / top_p and a given coin;
+        returns (token, gap) -- gap: relative distance of the decision from its nearest boundary."""
+        x = np.array(logits, np.float32, copy=True)
+        g = C.c_float(0)
+        tok = self.lib.orc_sample(_fp(x), C.c_int(x.size), C.c_float(temperature), C.c_float(top_p), C.c_float(coin), C.byref(g))
+        return int(tok), float(g.value)
+
+    def xorshift_floats(self, seed: int, n: int):
+        st = C.c_uint64(seed)
+        out = [float(self.lib.orc_xorshift_float(C.byref(st))) for _ in range(n)]
+        return out, int(st.value)
 
     # -- model ----------------------------------------------------------
     def open(self, path: str, seq_len: int = 0, trace: bool = False) -> "OracleModel":
@@ -348,3 +374,46 @@ class RefLib:
 
     def close(self, m):
         self.lib.model_free(m)
+
+
+class RefSampler:
+    """The reference's own sampler.c + xorshift.c, compiled unchanged (oracle/_ref/libqwen3_ref_sampler.so)."""
+
+    class _S(C.Structure):  # reference include/sampler.h:20-26
+        _fields_ = [("dist", C.c_void_p), ("seed", C.c_uint64), ("temperature", C.c_float), ("top_p", C.c_float),
+                    ("vocab_size", C.c_int)]
+
+    PATH = os.path.join(REF_DIR, "libqwen3_ref_sampler.so")
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(RefSampler.PATH)
+
+    def __init__(self):
+        L = C.CDLL(self.PATH)
+        L.sampler_create.restype = C.POINTER(self._S)
+        L.sampler_create.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint64]
+        L.sampler_free.argtypes = [C.POINTER(self._S)]
+        L.sample.restype = C.c_int
+        L.sample.argtypes = [C.POINTER(self._S), c_float_p]
+        L.xorshift_float.restype = C.c_float
+        L.xorshift_float.argtypes = [C.POINTER(C.c_uint64)]
+        self.lib = L
+
+    def create(self, vocab: int, temperature: float, top_p: float, seed: int):
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2)
+        os.dup2(devnull, 2)  # the reference prints its settings on stderr
+        try:
+            return self.lib.sampler_create(vocab, temperature, top_p, seed)
+        finally:
+            os.dup2(saved, 2)
+            os.close(saved)
+            os.close(devnull)
+
+    def sample(self, s, logits) -> int:
+        x = np.array(logits, np.float32, copy=True)
+        return int(self.lib.sample(s, _fp(x)))
+
+    def free(self, s):
+        self.lib.sampler_free(s)

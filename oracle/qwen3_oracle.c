@@ -441,3 +441,92 @@ int orc_argmax(const float* v, int n, float* margin) {
     }
     return best;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler: restatement of reference src/sampler.c and src/xorshift.c. Test
+ * infrastructure for the device sampler (qwen_cuda_sample); never part of the product path.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* reference src/xorshift.c:7-12 */
+uint32_t orc_xorshift_int32(uint64_t* state) {
+    *state ^= *state >> 12;
+    *state ^= *state << 25;
+    *state ^= *state >> 27;
+    return (uint32_t) ((*state * 0x2545F4914F6CDD1Dull) >> 32);
+}
+/* reference src/xorshift.c:14-16: 24 random bits -> [0, 1) */
+float orc_xorshift_float(uint64_t* state) { return (float) (orc_xorshift_int32(state) >> 8) / 16777216.0f; }
+
+/* reference src/sampler.c:34-52: the clamps sampler_create applies to top_p and temperature */
+void orc_sampler_clamp(float* temperature, float* top_p) {
+    const float epsilon = 1e-6f;
+    float p = *top_p, t = *temperature;
+    if (p > 1.0f || isnan(p) || 1 == isinf(p)) p = 1.0f;
+    else if (p < epsilon || -1 == isinf(p)) p = epsilon;
+    if (isnan(t) || 1 == isinf(t)) t = 1.0f;
+    else if (t < epsilon || -1 == isinf(t)) t = epsilon;
+    *top_p = p;
+    *temperature = t;
+}
+
+typedef struct { float sample; int index; } OrcProb; /* reference include/sampler.h:15-18 */
+
+/* reference src/sampler.c:139-149 (descending by probability; equal elements compare equal) */
+static int orc_cmp_dist(const void* a, const void* b) {
+    const OrcProb* n = (const OrcProb*) a;
+    const OrcProb* m = (const OrcProb*) b;
+    if (n->sample > m->sample) return -1;
+    if (n->sample < m->sample) return 1;
+    return 0;
+}
+
+/* reference src/sampler.c:186-201 (sample) with :164-178 (sampler_top_p), :88-113 (sampler_mass_index) and
+ * :126-136 (sampler_cdf_index) inlined. logits[] is overwritten with the probabilities like the reference does.
+ * temperature / top_p are the already clamped values. `gap` (optional) receives how far r = coin * mass is from the
+ * nearest cdf boundary it was compared with, and how far the cut-off mass is from top_p -- the smaller of the two,
+ * relative: a device sampler whose probabilities differ in the last bits may legitimately pick a neighbour when
+ * the gap is ~1e-6. Returns the token, or -1 if the scratch allocation fails. */
+int orc_sample(float* logits, int vocab_size, float temperature, float top_p, float coin, float* gap) {
+    for (int q = 0; q < vocab_size; q++) logits[q] /= temperature;
+    orc_softmax(logits, vocab_size);
+    OrcProb* dist = (OrcProb*) malloc((size_t) vocab_size * sizeof(OrcProb));
+    if (!dist) return -1;
+    for (int i = 0; i < vocab_size; i++) {
+        dist[i].index = i;
+        dist[i].sample = logits[i];
+    }
+    qsort(dist, (size_t) vocab_size, sizeof(OrcProb), orc_cmp_dist);
+    /* sampler_mass_index */
+    float mass = 0.0f, g = INFINITY;
+    int id = vocab_size - 1;
+    for (int i = 0; i < vocab_size; i++) {
+        const float before = mass;
+        mass += dist[i].sample;
+        if (mass > top_p) {
+            id = i;
+            g = fminf(fabsf(mass - top_p), fabsf(top_p - before)) / fmaxf(top_p, 1e-30f);
+            break;
+        }
+    }
+    const float epsilon = 1e-3f;
+    if (mass < epsilon) {
+        for (int i = 0; i <= id; i++) mass += dist[i].sample;
+    }
+    /* sampler_cdf_index(dist, n = id, coin, mass): note the inclusive bound i <= n and the fallback dist[n - 1] */
+    float cdf = 0.0f;
+    const float r = coin * mass;
+    int tok = -2;
+    for (int i = 0; i <= id; i++) {
+        cdf += dist[i].sample;
+        if (r < cdf) {
+            tok = dist[i].index;
+            const float lo = cdf - dist[i].sample;
+            g = fminf(g, fminf(fabsf(cdf - r), fabsf(r - lo)) / fmaxf(mass, 1e-30f));
+            break;
+        }
+    }
+    if (tok == -2) tok = dist[id > 0 ? id - 1 : 0].index; /* reference reads dist[n - 1]; n = 0 would read dist[-1] */
+    if (gap) *gap = g;
+    free(dist);
+    return tok;
+}

@@ -90,6 +90,12 @@ float* orc_forward(OrcModel* m, int token, int pos);
 /* argmax with lowest-index tie break; margin = top1 - top2 (H7 bookkeeping). */
 int orc_argmax(const float* v, int n, float* margin);
 
+/* sampler restatement (reference src/sampler.c, src/xorshift.c) */
+uint32_t orc_xorshift_int32(uint64_t* state);
+float orc_xorshift_float(uint64_t* state);
+void orc_sampler_clamp(float* temperature, float* top_p);
+int orc_sample(float* logits, int vocab_size, float temperature, float top_p, float coin, float* gap);
+
 #ifdef __cplusplus
 }
 #endif
