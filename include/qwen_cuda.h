@@ -112,6 +112,18 @@ int qwen_cuda_prefill(QwenCudaCtx* ctx, const int* tokens, int n, int pos0, floa
  * n argmax tokens. Stands behind the completion loop's forward+sample pair when the
  * sampler is greedy (reference: src/completion.c:57-66). */
 int qwen_cuda_decode_greedy(QwenCudaCtx* ctx, int first_token, int pos0, int n, int* out_tokens_host);
+/* Stands behind sample() (reference: src/sampler.c:186-201: logits /= temperature, softmax, top-p, inverse CDF)
+ * for the logits the LAST step of `ctx` left on the device: returns one token id instead of vocab_size floats.
+ * temperature / top_p as stored in the reference's Sampler (sampler_create's clamps are re-applied); `coin` is the
+ * caller's xorshift_float(&sampler->seed) (reference: src/xorshift.c:14-16), so the RNG stream stays the host's.
+ * Returns 0 and *token_out; 1 when the fast path does not apply (more than 4096 tokens could be in the nucleus:
+ * nearly flat distribution or top_p == 1) -- then copy the logits with qwen_cuda_logits_to_host and call the
+ * reference's sample(); negative on errors. The token is also left on the device for qwen_cuda_decode_greedy-style
+ * chaining. */
+int qwen_cuda_sample(QwenCudaCtx* ctx, float temperature, float top_p, float coin, int* token_out);
+/* Test hook: the same kernel on host logits. */
+int qwen_cuda_sample_host(const float* logits_host, int vocab_size, float temperature, float top_p, float coin,
+                          int* token_out);
 /* Device-timed decode for bench.py: `warmup` untimed then `steps` timed steps at
  * positions pos0, pos0+1, ... (token fixed), CUDA events on the context's stream.
  * *ms_total = device milliseconds for the timed steps; *launches = kernels launched. */

@@ -104,6 +104,8 @@ class QwenLib:
         L.qwen_cuda_sync.argtypes = [C.c_void_p]
         L.qwen_cuda_set_path.argtypes = [C.c_void_p, C.c_int]
         L.qwen_cuda_get_path.argtypes = [C.c_void_p]
+        L.qwen_cuda_sample.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, c_int32_p]
+        L.qwen_cuda_sample_host.argtypes = [c_float_p, C.c_int, C.c_float, C.c_float, C.c_float, c_int32_p]
         L.qwen_cuda_kv_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_kv_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_debug_set_layers.argtypes = [C.c_void_p, C.c_int]
@@ -113,6 +115,15 @@ class QwenLib:
         L.qwen_cuda_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_matmul_batch.argtypes = [c_float_p, c_int32_p, c_int8_p, c_float_p, c_int8_p, c_float_p, C.c_int, C.c_int,
                                              C.c_int, C.c_int, c_float_p]
+
+    def sample_host(self, logits, temperature: float, top_p: float, coin: float):
+        """Device sampler on host logits (test hook): returns the token, or None when the fast path does not apply."""
+        x = np.ascontiguousarray(logits, np.float32)
+        tok = C.c_int32(-1)
+        rc = self.lib.qwen_cuda_sample_host(_fp(x), x.size, temperature, top_p, coin, C.byref(tok))
+        if rc < 0:
+            raise RuntimeError("sample_host: " + self.err())
+        return int(tok.value) if rc == 0 else None
 
     def err(self) -> str:
         return (self.lib.qwen_cuda_last_error() or b"").decode()
@@ -235,6 +246,14 @@ class B200Model:
 
     def set_path(self, path: int):
         self.ql._ok(self.ql.lib.qwen_cuda_set_path(self.ctx, path), "set_path")
+
+    def sample(self, temperature: float, top_p: float, coin: float):
+        """sample() on the device logits of the last step (reference src/sampler.c:186-201); None = use the host path."""
+        tok = C.c_int32(-1)
+        rc = self.ql.lib.qwen_cuda_sample(self.ctx, temperature, top_p, coin, C.byref(tok))
+        if rc < 0:
+            raise RuntimeError("sample: " + self.ql.err())
+        return int(tok.value) if rc == 0 else None
 
     def get_path(self) -> int:
         return int(self.ql.lib.qwen_cuda_get_path(self.ctx))

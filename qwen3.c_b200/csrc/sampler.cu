@@ -1,0 +1,206 @@
+// sampler.cu -- device fast path for the reference sampler: sample() of src/sampler.c:186-201
+// (temperature, softmax, nucleus / top-p, inverse CDF with a host-supplied coin) on the logits the decode step left
+// in HBM, returning ONE token id instead of vocab_size floats. The reference copies 608 KB of logits to the host,
+// scales, exponentiates and qsorts all 151 936 entries per token (~11 ms); only the head of the sorted order can ever
+// be chosen, so the device sorts just that head.
+//
+// One CTA, 1024 threads, four passes over the logits in L2:
+//   1. m = max(l_i / T)                                   (sampler.c:188-190, forward.c:36-50)
+//   2. s = sum expf(l_i / T - m)                          (forward.c:53-69; tree order instead of serial)
+//   3. p_i = expf(l_i / T - m) / s; candidates = { p_i >= cut } with cut = 0.5 * (1 - top_p) / (V - 1): an entry
+//      below (1 - top_p) / (V - 1) cannot lie in the smallest prefix whose mass exceeds top_p, so the candidates are
+//      a prefix of the reference's sorted array that contains the whole nucleus; if more than kMaxCand entries pass,
+//      the cut is raised (x4 per round) until they fit -- still a prefix, and step 4 checks that the nucleus closes in it
+//   4. bitonic sort of the candidates (descending p, ascending index among equals -- the reference's order among
+//      equals is whatever qsort does), then ONE thread walks them exactly like sampler_mass_index (sampler.c:88-113,
+//      including the "heal" step) and sampler_cdf_index (sampler.c:126-136, inclusive bound and fallback).
+// status 1 = not handled (more than kMaxCand candidates: a nearly flat distribution or top_p == 1): the caller then
+// uses the reference's sample() on the host logits. Probabilities differ from the host's in the last bits (expf,
+// summation order), so a decision within ~1e-6 of a boundary may fall on the neighbouring token; tests bound that.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kMaxCand = 4096;
+
+__device__ __forceinline__ bool before(float pa, int ia, float pb, int ib) { return pa > pb || (pa == pb && ia < ib); }
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int i = 1; i < kThreads / 32; ++i) r = is_max ? fmaxf(r, red[i]) : __fadd_rn(r, red[i]);
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_sample(const float* __restrict__ logits, int V, float temperature, float top_p, float coin, int* __restrict__ out, int* token_dev) {
+    __shared__ float red[32];
+    __shared__ float sp[kMaxCand];
+    __shared__ int si[kMaxCand];
+    __shared__ int count;
+    const int tid = threadIdx.x;
+    if (tid == 0) count = 0;
+    // 1. max of the scaled logits
+    float m = -INFINITY;
+    for (int i = tid; i < V; i += kThreads) m = fmaxf(m, __fdiv_rn(logits[i], temperature));
+    m = block_reduce(m, red, true);
+    // 2. sum of exponentials
+    float s = 0.0f;
+    for (int i = tid; i < V; i += kThreads) s = __fadd_rn(s, expf(__fsub_rn(__fdiv_rn(logits[i], temperature), m)));
+    s = block_reduce(s, red, false);
+    // 3. candidates
+    float cut = V > 1 ? 0.5f * __fdiv_rn(__fsub_rn(1.0f, top_p), (float) (V - 1)) : 0.0f;
+    // { p >= cut } is a prefix of the sorted order for ANY cut, and the walk below verifies that the nucleus closes
+    // inside it; so when the safe cut leaves more than kMaxCand candidates (long flat tails), raise it until they fit
+    for (int round = 0; round < 24; ++round) {
+        int mine = 0;
+        for (int i = tid; i < V; i += kThreads) {
+            const float p = __fdiv_rn(expf(__fsub_rn(__fdiv_rn(logits[i], temperature), m)), s);
+            mine += (p >= cut && p > 0.0f) ? 1 : 0;
+        }
+        const int total = (int) block_reduce((float) mine, red, false); // counts < 2^24: exact in fp32
+        if (total <= kMaxCand) break;
+        cut = fmaxf(cut * 4.0f, 1e-30f);
+    }
+    for (int i = tid; i < V; i += kThreads) {
+        const float p = __fdiv_rn(expf(__fsub_rn(__fdiv_rn(logits[i], temperature), m)), s);
+        if (p >= cut && p > 0.0f) {
+            const int k = atomicAdd(&count, 1);
+            if (k < kMaxCand) {
+                sp[k] = p;
+                si[k] = i;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = count;
+    if (n > kMaxCand || n == 0) {
+        if (tid == 0) {
+            out[0] = -1;
+            out[1] = 1; // not handled
+        }
+        return;
+    }
+    // 4. bitonic sort of the n candidates padded to a power of two
+    int N = 2;
+    while (N < n) N <<= 1;
+    for (int i = n + tid; i < N; i += kThreads) {
+        sp[i] = -1.0f; // sorts behind everything
+        si[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < N; i += kThreads) {
+                const int x = i ^ j;
+                if (x > i) {
+                    const float pa = sp[i], pb = sp[x];
+                    const int ia = si[i], ib = si[x];
+                    const bool up = (i & k) == 0;
+                    if (up ? before(pb, ib, pa, ia) : before(pa, ia, pb, ib)) {
+                        sp[i] = pb; si[i] = ib;
+                        sp[x] = pa; si[x] = ia;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid != 0) return;
+    // sampler_mass_index over the sorted head
+    float mass = 0.0f;
+    int id = -1;
+    for (int i = 0; i < n; ++i) {
+        mass = __fadd_rn(mass, sp[i]);
+        if (mass > top_p) {
+            id = i;
+            break;
+        }
+    }
+    if (id < 0) { // the nucleus reaches past the candidates (top_p ~ 1): let the host path decide
+        out[0] = -1;
+        out[1] = 1;
+        return;
+    }
+    if (mass < 1e-3f)
+        for (int i = 0; i <= id; ++i) mass = __fadd_rn(mass, sp[i]);
+    // sampler_cdf_index(dist, n = id, coin, mass)
+    float cdf = 0.0f;
+    const float r = __fmul_rn(coin, mass);
+    int tok = -2;
+    for (int i = 0; i <= id; ++i) {
+        cdf = __fadd_rn(cdf, sp[i]);
+        if (r < cdf) {
+            tok = si[i];
+            break;
+        }
+    }
+    if (tok == -2) tok = si[id > 0 ? id - 1 : 0];
+    out[0] = tok;
+    out[1] = 0;
+    if (token_dev) *token_dev = tok;
+}
+
+void clamp_like_sampler_create(float& temperature, float& top_p) { // reference src/sampler.c:34-52
+    const float epsilon = 1e-6f;
+    if (top_p > 1.0f || isnan(top_p) || (isinf(top_p) && top_p > 0)) top_p = 1.0f;
+    else if (top_p < epsilon || (isinf(top_p) && top_p < 0)) top_p = epsilon;
+    if (isnan(temperature) || (isinf(temperature) && temperature > 0)) temperature = 1.0f;
+    else if (temperature < epsilon || (isinf(temperature) && temperature < 0)) temperature = epsilon;
+}
+
+int run_sample(const float* logits_dev, int V, float temperature, float top_p, float coin, int* out_dev, int* token_dev,
+               cudaStream_t st, int* token_out) {
+    clamp_like_sampler_create(temperature, top_p);
+    k_sample<<<1, kThreads, 0, st>>>(logits_dev, V, temperature, top_p, coin, out_dev, token_dev);
+    QW_CUDA(cudaGetLastError());
+    int res[2] = {-1, -1};
+    QW_CUDA(cudaMemcpyAsync(res, out_dev, sizeof res, cudaMemcpyDeviceToHost, st));
+    QW_CUDA(cudaStreamSynchronize(st));
+    if (res[1] == 0) {
+        *token_out = res[0];
+        return 0;
+    }
+    *token_out = -1;
+    return 1;
+}
+
+} // namespace
+
+// Stands behind sample() (reference: src/sampler.c:186-201) for the logits of the context's last step.
+extern "C" int qwen_cuda_sample(QwenCudaCtx* c, float temperature, float top_p, float coin, int* token_out) {
+    if (!c || !token_out) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    const float* src = c->tp_size > 1 ? c->logits_all : c->logits;
+    // argmax_out doubles as the 2-int result slot (its first entries are rewritten by every greedy chain anyway)
+    return run_sample(src, c->V, temperature, top_p, coin, c->argmax_out, c->token_dev, c->stream, token_out);
+}
+
+// Context-free variant for tests: host logits in, token out.
+extern "C" int qwen_cuda_sample_host(const float* logits_host, int vocab_size, float temperature, float top_p, float coin,
+                                     int* token_out) {
+    if (!logits_host || !token_out || vocab_size <= 0) return -2;
+    if (qwen_cuda_device_count() <= 0) {
+        qw_set_error("no CUDA device: this library has no CPU path");
+        return -1;
+    }
+    float* d = nullptr;
+    int* o = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc((void**) &d, (size_t) vocab_size * 4) || cudaMalloc((void**) &o, 16)) break;
+        if (cudaMemcpy(d, logits_host, (size_t) vocab_size * 4, cudaMemcpyHostToDevice)) break;
+        rc = run_sample(d, vocab_size, temperature, top_p, coin, o, nullptr, 0, token_out);
+    } while (0);
+    if (rc < 0) qw_set_error("sample_host: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    cudaFree(o);
+    return rc;
+}

@@ -575,3 +575,60 @@ def test_4b_full_shape_first_tokens(qlib, oracle, pkg, ckpt_dir):
     with qlib.open(path, 16) as gm:
         lg = gm.forward_prefill(toks, 0)
         assert np.abs(lg - ref[-1]).max() < 0.05 * max(1.0, ref[-1].std())
+
+
+# ---------------------------------------------------------------- device sampler
+def test_device_sampler_matches_reference_sampler(qlib, oracle):
+    """qwen_cuda_sample_host (csrc/sampler.cu) against the oracle's restatement of sample() (reference src/sampler.c:186-201,
+    pinned to the compiled reference in tests/test_sampler_oracle.py) on seeded logits: same token for the same coin.
+    The device probabilities differ from the host's in the last bits (expf, summation order), so a token may differ only
+    when the oracle reports that the decision sat within 1e-5 (relative) of a boundary -- and that must be rare."""
+    rng = np.random.default_rng(2024)
+    total = near = 0
+    for V in (512, 4096, 151936):
+        for t, p in ((1.0, 0.9), (0.7, 0.8), (1e-6, 0.9), (1.5, 0.95), (0.3, 0.5), (1.0, 1e-6)):
+            ct, cp = oracle.sampler_clamp(t, p)
+            for rep in range(6 if V < 100000 else 3):
+                lg = (rng.standard_normal(V) * float(rng.choice([2.0, 6.0, 12.0]))).astype(np.float32)
+                coin = float(np.float32(rng.random()))
+                want, gap = oracle.sample(lg, ct, cp, coin)
+                got = qlib.sample_host(lg, ct, cp, coin)
+                if got is None:  # declined: only when the nucleus itself can exceed 4096 tokens (big vocabulary, flat distribution)
+                    assert V > 4096 and float(lg.std()) / ct < 4.5, (V, t, p)
+                    continue
+                total += 1
+                if got != want:
+                    near += 1
+                    assert gap < 1e-5, (V, t, p, coin, got, want, gap)
+    assert total > 60 and near <= 2, (total, near)
+
+
+def test_device_sampler_declines_flat_and_top_p_one(qlib, oracle):
+    """More than 4096 tokens can lie in the nucleus: the kernel reports 'not handled' (the caller then runs the
+    reference's sample() on host logits) instead of guessing."""
+    V = 20000
+    flat = np.zeros(V, np.float32)
+    assert qlib.sample_host(flat, 1.0, 0.9, 0.5) is None
+    lg = (np.random.default_rng(1).standard_normal(V) * 4).astype(np.float32)
+    assert qlib.sample_host(lg, 1.0, 1.0, 0.5) is None
+    assert qlib.sample_host(lg, 1.0, 0.9, 0.5) == oracle.sample(lg, 1.0, 0.9, 0.5)[0]
+    one_hot = np.full(V, -30.0, np.float32)
+    one_hot[1234] = 30.0
+    for coin in (0.0, 0.999):
+        assert qlib.sample_host(one_hot, 1.0, 0.9, coin) == 1234
+
+
+def test_device_sampler_on_context_logits(qlib, oracle, pkg, ckpt_dir):
+    """qwen_cuda_sample on the logits of the last forward(): same tokens as the oracle sampler fed with the host copy of
+    those logits and the same xorshift coins; the sampled token drives the next step (a short sampled generation)."""
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "small", seed=11)
+    coins, _ = oracle.xorshift_floats(99, 12)
+    ct, cp = oracle.sampler_clamp(0.8, 0.9)
+    with qlib.open(path, 32) as gm:
+        tok = 5
+        for pos in range(12):
+            lg = gm.forward(tok, pos)
+            want, gap = oracle.sample(lg, ct, cp, coins[pos])
+            got = gm.sample(ct, cp, coins[pos])
+            assert got is not None and (got == want or gap < 1e-5), (pos, got, want, gap)
+            tok = want
