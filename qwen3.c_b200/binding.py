@@ -247,6 +247,10 @@ class B200Model:
     def set_path(self, path: int):
         self.ql._ok(self.ql.lib.qwen_cuda_set_path(self.ctx, path), "set_path")
 
+    def forward_async(self, token: int, pos: int) -> None:
+        """Enqueue one decode step; the logits stay on the device (qwen_cuda_forward_async)."""
+        self.ql._ok(self.ql.lib.qwen_cuda_forward_async(self.ctx, token, pos), "forward_async")
+
     def sample(self, temperature: float, top_p: float, coin: float):
         """sample() on the device logits of the last step (reference src/sampler.c:186-201); None = use the host path."""
         tok = C.c_int32(-1)
