@@ -7,7 +7,7 @@
 // One CTA, 1024 threads, four passes over the logits in L2:
 //   1. m = max(l_i / T)                                   (sampler.c:188-190, forward.c:36-50)
 //   2. s = sum expf(l_i / T - m)                          (forward.c:53-69; tree order instead of serial)
-//   3. p_i = expf(l_i / T - m) / s; candidates = { p_i >= cut } with cut = 0.5 * (1 - top_p) / (V - 1): an entry
+//   3. p_i = expf(l_i / T - m) / s; candidates = { p_i >= cut } (tested in the log domain) with cut = 0.5 * (1 - top_p) / (V - 1): an entry
 //      below (1 - top_p) / (V - 1) cannot lie in the smallest prefix whose mass exceeds top_p, so the candidates are
 //      a prefix of the reference's sorted array that contains the whole nucleus; if more than kMaxCand entries pass,
 //      the cut is raised (x4 per round) until they fit -- still a prefix, and step 4 checks that the nucleus closes in it
@@ -47,34 +47,39 @@ k_sample(const float* __restrict__ logits, int V, float temperature, float top_p
     __shared__ int count;
     const int tid = threadIdx.x;
     if (tid == 0) count = 0;
-    // 1. max of the scaled logits
+    // 1. max of the scaled logits: division by T > 0 is monotone, so max(l_i / T) = max(l_i) / T exactly
     float m = -INFINITY;
-    for (int i = tid; i < V; i += kThreads) m = fmaxf(m, __fdiv_rn(logits[i], temperature));
-    m = block_reduce(m, red, true);
+    for (int i = tid; i < V; i += kThreads) m = fmaxf(m, logits[i]);
+    m = __fdiv_rn(block_reduce(m, red, true), temperature);
     // 2. sum of exponentials
     float s = 0.0f;
     for (int i = tid; i < V; i += kThreads) s = __fadd_rn(s, expf(__fsub_rn(__fdiv_rn(logits[i], temperature), m)));
     s = block_reduce(s, red, false);
-    // 3. candidates
-    float cut = V > 1 ? 0.5f * __fdiv_rn(__fsub_rn(1.0f, top_p), (float) (V - 1)) : 0.0f;
-    // { p >= cut } is a prefix of the sorted order for ANY cut, and the walk below verifies that the nucleus closes
-    // inside it; so when the safe cut leaves more than kMaxCand candidates (long flat tails), raise it until they fit
-    for (int round = 0; round < 24; ++round) {
+    // 3. candidates. The membership test runs on z_i = l_i / T - m against theta = log(cut * s): monotone in p_i, so
+    // { z_i >= theta } is a prefix of the sorted order for ANY theta (up to the order among equal probabilities, which
+    // the reference leaves to qsort), and the walk below verifies that the nucleus closes inside it. theta starts at
+    // the safe cut (nothing below (1 - top_p) / (V - 1) can be in the nucleus; half of that here) and is raised until
+    // at most kMaxCand entries pass (long flat tails). Only the candidates' probabilities are computed again.
+    const float cut = V > 1 ? 0.5f * __fdiv_rn(__fsub_rn(1.0f, top_p), (float) (V - 1)) : 0.0f;
+    float theta = cut > 0.0f ? logf(cut * s) : -INFINITY;
+    theta = fmaxf(theta, -87.0f); // expf underflows to 0 below: such entries can never be chosen
+    for (int round = 0; round < 64; ++round) {
         int mine = 0;
-        for (int i = tid; i < V; i += kThreads) {
-            const float p = __fdiv_rn(expf(__fsub_rn(__fdiv_rn(logits[i], temperature), m)), s);
-            mine += (p >= cut && p > 0.0f) ? 1 : 0;
-        }
+        for (int i = tid; i < V; i += kThreads) mine += __fsub_rn(__fdiv_rn(logits[i], temperature), m) >= theta ? 1 : 0;
         const int total = (int) block_reduce((float) mine, red, false); // counts < 2^24: exact in fp32
         if (total <= kMaxCand) break;
-        cut = fmaxf(cut * 4.0f, 1e-30f);
+        theta += 1.0f; // e times fewer probability mass per step
     }
     for (int i = tid; i < V; i += kThreads) {
-        const float p = __fdiv_rn(expf(__fsub_rn(__fdiv_rn(logits[i], temperature), m)), s);
-        if (p >= cut && p > 0.0f) {
+        const float z = __fsub_rn(__fdiv_rn(logits[i], temperature), m);
+        if (z >= theta) {
+            const float p = __fdiv_rn(expf(z), s);
             const int k = atomicAdd(&count, 1);
-            if (k < kMaxCand) {
+            if (k < kMaxCand && p > 0.0f) {
                 sp[k] = p;
+                si[k] = i;
+            } else if (k < kMaxCand) { // keep the slot dense: a zero-probability entry sorts last and is never chosen
+                sp[k] = 0.0f;
                 si[k] = i;
             }
         }
