@@ -632,3 +632,56 @@ def test_device_sampler_on_context_logits(qlib, oracle, pkg, ckpt_dir):
             got = gm.sample(ct, cp, coins[pos])
             assert got is not None and (got == want or gap < 1e-5), (pos, got, want, gap)
             tok = want
+
+
+# ---------------------------------------------------------------- the reference's own CLI on our library (config 1)
+def _oracle_completion(oracle, path, ids, n_ctx, temperature, top_p, seed):
+    """The reference's completion loop (src/completion.c:57-87) on the oracle: teacher-forced prompt, then sample();
+    returns the tokens it prints and how close the run came to a decision boundary (smallest top-2 logit margin and
+    smallest relative distance of a coin from a cumulative-mass boundary)."""
+    ct, cp = oracle.sampler_clamp(temperature, top_p)
+    coins, _ = oracle.xorshift_floats(seed, n_ctx)
+    toks, min_margin, min_gap, ci = [], 1e9, 1e9, 0
+    with oracle.open(path, n_ctx) as om:
+        tok = ids[0]
+        for pos in range(n_ctx):
+            lo = om.forward(tok, pos)
+            toks.append(tok)
+            if pos + 1 < len(ids):
+                nxt = ids[pos + 1]
+            else:
+                nxt, gap = oracle.sample(lo, ct, cp, coins[ci])
+                ci += 1
+                min_margin = min(min_margin, oracle.argmax(lo)[1])
+                min_gap = min(min_gap, gap)
+            tok = nxt
+    return toks, min_margin, min_gap
+
+
+def test_reference_cli_unmodified_generates_the_same_text(qlib, oracle, pkg, ckpt_dir):
+    """BASELINE config 1 in miniature and the drop-in claim of SURVEY.md 8b as a running program: the reference's
+    UNMODIFIED examples/qwen.c + src/{qwen,completion,sampler,tokenizer,xorshift}.c, compiled against our headers and
+    linked against our libqwen3.so (oracle/_ref/qwen_b200, built by oracle/Makefile where the reference tree exists),
+    must print the same completion as the reference's own CPU build (oracle/_ref/qwen_ref): greedy (-t 0) and sampled
+    (-t 1 -p 0.9; every logit feeds the host sampler, so the streams match only if the logits do). The prompt / seed
+    are chosen so that the oracle's own run stays clear of decision boundaries (asserted), otherwise a one-code
+    re-quantisation flip could legitimately change a token."""
+    import subprocess
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours, ref = (os.path.join(here, "oracle", "_ref", n) for n in ("qwen_b200", "qwen_ref"))
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("oracle/_ref/qwen_b200 / qwen_ref not built (they need the reference tree at build time)")
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "tiny-untied", seed=11)
+    if not os.path.exists(path + ".tokenizer"):
+        pkg.checkpoint.write_tokenizer(path + ".tokenizer", pkg.checkpoint.SHAPES["tiny-untied"].vocab_size)
+    for prompt, n_ctx, t, p, seed in (("Qwen", 48, 0.0, 0.9, 1), ("abc", 20, 1.0, 0.9, 33)):
+        toks, margin, gap = _oracle_completion(oracle, path, [ord(ch) for ch in prompt], n_ctx, t, p, seed)
+        assert (margin > 0.05) if t == 0.0 else (gap > 3e-3), (prompt, margin, gap)  # the chosen run is a fair test
+        args = [path, "-m", "completion", "-i", prompt, "-c", str(n_ctx), "-t", str(t), "-p", str(p), "-s", str(seed)]
+        outs = []
+        for exe in (ref, ours):
+            r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            assert r.returncode == 0, (exe, r.stderr[-800:])
+            outs.append(r.stdout)
+        assert len(set(toks)) > 8, "degenerate completion: not a useful comparison"
+        assert outs[0] == outs[1], (prompt, outs[0][:200], outs[1][:200])
