@@ -18,9 +18,11 @@
 //     word of the arena starts as a sentinel bit pattern that no computation can produce
 //     (a signalling NaN whose low bytes are the int8 code -128, which the quantiser never
 //     emits). A producer simply stores its result; a consumer polls the words it needs with
-//     ld.relaxed.gpu until none is the sentinel. No flags, no fences, no counters: one store
+//     ld.relaxed.gpu until none is the sentinel. No flags, no counters: one store
 //     latency plus one L2 round trip per hand-off, and a CTA starts a phase the moment ITS
-//     inputs exist. Every (layer, vector) has its own slot in the arena, so each word is
+//     inputs exist. Results leave an SM as ONE TMA bulk store per CTA (cp.async.bulk from a
+//     shared-memory staging area: GEMV rows and attention partials are contiguous in the arena),
+//     so no warp waits in a fence and the stores do not queue behind the polling loads. Every (layer, vector) has its own slot in the arena, so each word is
 //     written exactly once per launch and there is no write-after-read hazard inside a launch;
 //     two arenas alternate between launches and each launch refills the other one with the
 //     sentinel for the next launch (stream order makes that refill complete before it is used).
@@ -31,6 +33,12 @@
 // online-softmax over its share of the positions with no cross-warp synchronisation, the CTA merges its
 // 15 warp states in shared memory and publishes one partial per head; (head, half) combine tasks
 // merge the partials of a head and write the attention output already quantised for wo.
+//
+// Tensor parallelism (k_decode<KV_MUL, true>, one process per GPU): the all-reduce after wo / w2 is
+// part of the dataflow. Every rank's arenas are mapped into every process (cudaIpc, NVLink peer
+// access); the wo / w2 epilogue bulk-stores the CTA's partial sums into slot tp_rank of EVERY rank's
+// arena, and the next prologue adds the tp slots in rank order to the residual stream that each CTA
+// keeps in shared memory -- bit-identical x on all ranks, no collective call, no extra launch.
 //
 // Every wait in this file has a wall-clock timeout that raises a sticky error flag
 // instead of hanging the GPU.
