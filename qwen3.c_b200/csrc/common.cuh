@@ -162,6 +162,7 @@ struct QwenCudaCtx {
     void* prefill;    // prefill activation buffers (prefill.cu), allocated on first use
     int layers_run;   // debug: run only the first n layers (-1 = all)
     float* logits_pinned; // optional pinned bounce buffer
+    float* sample_ws;     // workspace of the device sampler (sampler.cu), allocated on first use
     size_t bytes_weights, bytes_kv;
 };
 

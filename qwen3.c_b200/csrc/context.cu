@@ -212,6 +212,7 @@ extern "C" void qwen_cuda_destroy(QwenCudaCtx* c) {
     qw_prefill_free(c);
     qw_tp_free(c);
     if (c->logits_all) cudaFree(c->logits_all);
+    if (c->sample_ws) cudaFree(c->sample_ws);
     if (c->w_emb != c->w_cls) cudaFree(c->w_emb);
     void* bufs[] = {c->w_qkv, c->w_o, c->w_13, c->w_2, c->w_cls, c->att_norm, c->ffn_norm, c->out_norm, c->q_norm,
                     c->k_norm, c->rope_cos, c->rope_sin, c->k_cache, c->v_cache, c->x, c->xb, c->qkv, c->q, c->att,

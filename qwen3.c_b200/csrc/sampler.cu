@@ -17,9 +17,15 @@
 // status 1 = not handled (more than kMaxCand candidates: a nearly flat distribution or top_p == 1): the caller then
 // uses the reference's sample() on the host logits. Probabilities differ from the host's in the last bits (expf,
 // summation order), so a decision within ~1e-6 of a boundary may fall on the neighbouring token; tests bound that.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -38,6 +44,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
     for (int i = 1; i < kThreads / 32; ++i) r = is_max ? fmaxf(r, red[i]) : __fadd_rn(r, red[i]);
     return r;
 }
+
+__device__ __forceinline__ void sort_and_walk(float* sp, int* si, int n, float top_p, float coin, int* __restrict__ out, int* token_dev);
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_sample(const float* __restrict__ logits, int V, float temperature, float top_p, float coin, int* __restrict__ out, int* token_dev) {
@@ -93,6 +101,12 @@ k_sample(const float* __restrict__ logits, int V, float temperature, float top_p
         }
         return;
     }
+    sort_and_walk(sp, si, n, top_p, coin, out, token_dev);
+}
+
+// Steps 4 of the header comment: sort the n candidates in shared memory (sp / si), then one thread walks them.
+__device__ __forceinline__ void sort_and_walk(float* sp, int* si, int n, float top_p, float coin, int* __restrict__ out, int* token_dev) {
+    const int tid = threadIdx.x;
     // 4. bitonic sort of the n candidates padded to a power of two
     int N = 2;
     while (N < n) N <<= 1;
@@ -153,6 +167,82 @@ k_sample(const float* __restrict__ logits, int V, float temperature, float top_p
     if (token_dev) *token_dev = tok;
 }
 
+
+// The same computation spread over the whole chip (cooperative launch, one CTA per SM): every pass touches one or two
+// logits per thread and the passes meet at grid barriers. Opt-in (QWEN_SAMPLE_GRID=1): measured SLOWER than the
+// single CTA at vocabulary 151 936 (see run_sample); kept as the cross-check of the single-CTA kernel in the tests. Workspace (ints / floats, zeroed by block 0 at entry):
+//   [0 .. G) per-CTA maxima   [G .. 2G) per-CTA sums   [2G .. 2G+64) per-round counts   [2G+64] candidate counter
+//   then kMaxCand probabilities and kMaxCand indices. Sums are added in CTA order: deterministic.
+__global__ void __launch_bounds__(kThreads, 1)
+k_sample_grid(const float* __restrict__ logits, int V, float temperature, float top_p, float coin, int* __restrict__ out, int* token_dev,
+              float* __restrict__ ws) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float red[32];
+    __shared__ float sp[kMaxCand];
+    __shared__ int si[kMaxCand];
+    const int tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+    const int stride = G * kThreads, i0 = b * kThreads + tid;
+    float* pmax = ws;
+    float* psum = ws + G;
+    int* counts = reinterpret_cast<int*>(ws + 2 * G);
+    int* ncand = counts + 64;
+    float* cand_p = ws + 2 * G + 65;
+    int* cand_i = reinterpret_cast<int*>(cand_p + kMaxCand);
+    if (b == 0 && tid < 65) counts[tid] = 0;
+    float m = -INFINITY;
+    for (int i = i0; i < V; i += stride) m = fmaxf(m, logits[i]);
+    m = block_reduce(m, red, true);
+    if (tid == 0) pmax[b] = m;
+    grid.sync();
+    m = -INFINITY;
+    for (int i = 0; i < G; ++i) m = fmaxf(m, __ldcg(pmax + i));
+    m = __fdiv_rn(m, temperature);
+    float s = 0.0f;
+    for (int i = i0; i < V; i += stride) s = __fadd_rn(s, expf(__fsub_rn(__fdiv_rn(logits[i], temperature), m)));
+    s = block_reduce(s, red, false);
+    if (tid == 0) psum[b] = s;
+    grid.sync();
+    s = 0.0f;
+    for (int i = 0; i < G; ++i) s = __fadd_rn(s, __ldcg(psum + i));
+    const float cut = V > 1 ? 0.5f * __fdiv_rn(__fsub_rn(1.0f, top_p), (float) (V - 1)) : 0.0f;
+    float theta = cut > 0.0f ? logf(cut * s) : -INFINITY;
+    theta = fmaxf(theta, -87.0f);
+    int n = 0;
+    for (int round = 0; round < 64; ++round) {
+        int mine = 0;
+        for (int i = i0; i < V; i += stride) mine += __fsub_rn(__fdiv_rn(logits[i], temperature), m) >= theta ? 1 : 0;
+        const int blk = (int) block_reduce((float) mine, red, false);
+        if (tid == 0 && blk) atomicAdd(&counts[round], blk);
+        grid.sync();
+        n = *reinterpret_cast<volatile int*>(&counts[round]);
+        if (n <= kMaxCand) break;
+        theta += 1.0f;
+    }
+    if (n > kMaxCand || n == 0) { // uniform over the grid
+        if (b == 0 && tid == 0) {
+            out[0] = -1;
+            out[1] = 1;
+        }
+        return;
+    }
+    for (int i = i0; i < V; i += stride) {
+        const float z = __fsub_rn(__fdiv_rn(logits[i], temperature), m);
+        if (z >= theta) {
+            const int k = atomicAdd(ncand, 1);
+            cand_p[k] = __fdiv_rn(expf(z), s);
+            cand_i[k] = i;
+        }
+    }
+    grid.sync();
+    if (b != 0) return;
+    for (int i = tid; i < n; i += kThreads) { // plain loads after the grid barrier: written by other CTAs
+        sp[i] = __ldcg(cand_p + i);
+        si[i] = __ldcg(cand_i + i);
+    }
+    __syncthreads();
+    sort_and_walk(sp, si, n, top_p, coin, out, token_dev);
+}
+
 void clamp_like_sampler_create(float& temperature, float& top_p) { // reference src/sampler.c:34-52
     const float epsilon = 1e-6f;
     if (top_p > 1.0f || isnan(top_p) || (isinf(top_p) && top_p > 0)) top_p = 1.0f;
@@ -161,10 +251,23 @@ void clamp_like_sampler_create(float& temperature, float& top_p) { // reference 
     else if (temperature < epsilon || (isinf(temperature) && temperature < 0)) temperature = epsilon;
 }
 
+constexpr size_t kWsFloats = 2 * 256 + 65 + 2 * kMaxCand;
+
 int run_sample(const float* logits_dev, int V, float temperature, float top_p, float coin, int* out_dev, int* token_dev,
-               cudaStream_t st, int* token_out) {
+               float* ws, int num_sms, cudaStream_t st, int* token_out) {
     clamp_like_sampler_create(temperature, top_p);
-    k_sample<<<1, kThreads, 0, st>>>(logits_dev, V, temperature, top_p, coin, out_dev, token_dev);
+    // QWEN_SAMPLE_GRID=1 selects the cooperative multi-CTA kernel. Measured on B200 (4B shape, bench.py sampled_generation):
+    // single CTA 500 tok/s (the kernel costs ~0.12 ms), cooperative grid 447 tok/s (~0.36 ms: seven grid barriers of
+    // 148 x 1024 threads and the cooperative launch cost more than the passes save) -- so one CTA is the default.
+    const char* e = getenv("QWEN_SAMPLE_GRID");
+    int G = std::min(std::min(num_sms, 256), (V + kThreads - 1) / kThreads);
+    if (ws && G > 1 && e && atoi(e) == 1) {
+        void* args[] = {(void*) &logits_dev, (void*) &V, (void*) &temperature, (void*) &top_p, (void*) &coin, (void*) &out_dev,
+                        (void*) &token_dev, (void*) &ws};
+        QW_CUDA(cudaLaunchCooperativeKernel((const void*) k_sample_grid, dim3(G), dim3(kThreads), args, 0, st));
+    } else {
+        k_sample<<<1, kThreads, 0, st>>>(logits_dev, V, temperature, top_p, coin, out_dev, token_dev);
+    }
     QW_CUDA(cudaGetLastError());
     int res[2] = {-1, -1};
     QW_CUDA(cudaMemcpyAsync(res, out_dev, sizeof res, cudaMemcpyDeviceToHost, st));
@@ -184,8 +287,12 @@ extern "C" int qwen_cuda_sample(QwenCudaCtx* c, float temperature, float top_p, 
     if (!c || !token_out) return -2;
     QW_CUDA(cudaSetDevice(c->device));
     const float* src = c->tp_size > 1 ? c->logits_all : c->logits;
+    if (!c->sample_ws && cudaMalloc((void**) &c->sample_ws, kWsFloats * 4) != cudaSuccess) {
+        cudaGetLastError();
+        c->sample_ws = nullptr; // the single-CTA kernel needs no workspace
+    }
     // argmax_out doubles as the 2-int result slot (its first entries are rewritten by every greedy chain anyway)
-    return run_sample(src, c->V, temperature, top_p, coin, c->argmax_out, c->token_dev, c->stream, token_out);
+    return run_sample(src, c->V, temperature, top_p, coin, c->argmax_out, c->token_dev, c->sample_ws, c->num_sms, c->stream, token_out);
 }
 
 // Context-free variant for tests: host logits in, token out.
@@ -196,16 +303,20 @@ extern "C" int qwen_cuda_sample_host(const float* logits_host, int vocab_size, f
         qw_set_error("no CUDA device: this library has no CPU path");
         return -1;
     }
-    float* d = nullptr;
+    float *d = nullptr, *ws = nullptr;
     int* o = nullptr;
-    int rc = -1;
+    int rc = -1, sms = 1;
     do {
-        if (cudaMalloc((void**) &d, (size_t) vocab_size * 4) || cudaMalloc((void**) &o, 16)) break;
+        if (cudaMalloc((void**) &d, (size_t) vocab_size * 4) || cudaMalloc((void**) &o, 16) || cudaMalloc((void**) &ws, kWsFloats * 4)) break;
         if (cudaMemcpy(d, logits_host, (size_t) vocab_size * 4, cudaMemcpyHostToDevice)) break;
-        rc = run_sample(d, vocab_size, temperature, top_p, coin, o, nullptr, 0, token_out);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        rc = run_sample(d, vocab_size, temperature, top_p, coin, o, nullptr, ws, sms, 0, token_out);
     } while (0);
     if (rc < 0) qw_set_error("sample_host: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(d);
     cudaFree(o);
+    cudaFree(ws);
     return rc;
 }

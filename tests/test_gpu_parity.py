@@ -578,11 +578,14 @@ def test_4b_full_shape_first_tokens(qlib, oracle, pkg, ckpt_dir):
 
 
 # ---------------------------------------------------------------- device sampler
-def test_device_sampler_matches_reference_sampler(qlib, oracle):
-    """qwen_cuda_sample_host (csrc/sampler.cu) against the oracle's restatement of sample() (reference src/sampler.c:186-201,
+@pytest.mark.parametrize("grid_kernel", ["1", "0"])
+def test_device_sampler_matches_reference_sampler(qlib, oracle, grid_kernel, monkeypatch):
+    """Both kernels (QWEN_SAMPLE_GRID=1: cooperative, one CTA per SM; 0: single CTA).
+    qwen_cuda_sample_host (csrc/sampler.cu) against the oracle's restatement of sample() (reference src/sampler.c:186-201,
     pinned to the compiled reference in tests/test_sampler_oracle.py) on seeded logits: same token for the same coin.
     The device probabilities differ from the host's in the last bits (expf, summation order), so a token may differ only
     when the oracle reports that the decision sat within 1e-5 (relative) of a boundary -- and that must be rare."""
+    monkeypatch.setenv("QWEN_SAMPLE_GRID", grid_kernel)
     rng = np.random.default_rng(2024)
     total = near = 0
     for V in (512, 4096, 151936):
