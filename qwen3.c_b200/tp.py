@@ -47,10 +47,14 @@ class EmulatedRank:
     reference's primitives: rmsnorm, q8_quantize, matmul, rotary, swiglu, attention). It exists to
     check the SHARDING MATH on CPU (gloo tests); the GPU path is csrc/decode_ops.cu + NCCL."""
 
-    def __init__(self, views: dict, plan: ShardPlan, ops, allreduce, allgather, seq_len: int):
+    def __init__(self, views: dict, plan: ShardPlan, ops, allreduce, allgather, seq_len: int, rank_order: bool = False):
         import numpy as np
         self.np, self.v, self.p, self.ops = np, views, plan, ops
         self.allreduce, self.allgather = allreduce, allgather
+        # rank_order: the arithmetic of the FUSED device path (csrc/decode_mega.cu, kind 3): every rank receives all
+        # partial vectors and adds them to the residual stream one by one in rank order, x = ((x + p0) + p1) + ...,
+        # instead of x + allreduce(p) -- bit-identical on every rank by construction
+        self.rank_order = rank_order
         L, hd = views["n_layers"], views["head_dim"]
         self.kvd = len(plan.kv_rows)
         self.S = seq_len
@@ -69,6 +73,14 @@ class EmulatedRank:
         q = np.ascontiguousarray(q)
         s = np.ascontiguousarray(s)
         return self.ops.matmul(x_q, x_s, q.reshape(-1), s.reshape(-1), q.shape[1], q.shape[0])
+
+    def _residual_add(self, x, part):
+        if not self.rank_order:
+            return x + self.allreduce(part)
+        parts = self.allgather(part).reshape(self.p.size, -1)  # slot q = rank q's partial, as in the flow arena
+        for q in range(self.p.size):
+            x = (x + parts[q]).astype(self.np.float32)
+        return x
 
     def forward(self, token: int, pos: int):
         np, v, p, ops, hd = self.np, self.v, self.p, self.ops, self.hd
@@ -90,13 +102,13 @@ class EmulatedRank:
             att = ops.attention(q, self.k[l], self.vv[l], n_local_heads, n_local_kv, hd, self.S, pos)
             aq, as_ = ops.q8_quantize(att)
             part = self._mm(aq, as_, v["wo"][l], range(0, D), p.o_cols)
-            x = x + self.allreduce(part)
+            x = self._residual_add(x, part)
             xq, xs = ops.q8_quantize(ops.rmsnorm(x, v["ffn_norm"][l]))
             h1 = self._mm(xq, xs, v["w1"][l], p.hid_rows)
             h3 = self._mm(xq, xs, v["w3"][l], p.hid_rows)
             hq, hs = ops.q8_quantize(ops.swiglu(h1, h3))
             part = self._mm(hq, hs, v["w2"][l], range(0, D), p.hid_rows)
-            x = x + self.allreduce(part)
+            x = self._residual_add(x, part)
         xq, xs = ops.q8_quantize(ops.rmsnorm(x, v["out_norm"]))
         return self.allgather(self._mm(xq, xs, v["cls"], p.vocab_rows))
 

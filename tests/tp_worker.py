@@ -34,16 +34,24 @@ def main():
         return torch.cat(outs).numpy()
 
     S = 16
-    er = pkg.tp.EmulatedRank(views, plan, orc, allreduce, allgather, S)
     toks = [3, 77, 200, 9]
     worst = 0.0
-    with orc.open(path, S) as om:
-        for pos, t in enumerate(toks):
-            full = om.forward(t, pos)
-            mine = er.forward(t, pos)
-            worst = max(worst, float(np.abs(full - mine).max()))
-            assert int(full.argmax()) == int(mine.argmax()), (pos, rank)
-            assert np.all(np.abs(full - mine) <= 1e-2 + 1e-3 * np.abs(full)), (pos, rank, worst)
+    # both ways of forming the residual stream: x + allreduce(p) (per-op + NCCL path) and the fused device path's
+    # rank-order sum over the gathered partials
+    for rank_order in (False, True):
+        er = pkg.tp.EmulatedRank(views, plan, orc, allreduce, allgather, S, rank_order=rank_order)
+        with orc.open(path, S) as om:
+            for pos, t in enumerate(toks):
+                full = om.forward(t, pos)
+                mine = er.forward(t, pos)
+                worst = max(worst, float(np.abs(full - mine).max()))
+                assert int(full.argmax()) == int(mine.argmax()), (pos, rank)
+                assert np.all(np.abs(full - mine) <= 1e-2 + 1e-3 * np.abs(full)), (pos, rank, worst)
+                if rank_order:  # every rank must hold the same bits
+                    tt = torch.from_numpy(mine.copy())
+                    ref = tt.clone()
+                    dist.broadcast(ref, src=0)
+                    assert torch.equal(tt, ref), (pos, rank)
     # every rank sees identical logits (all-reduce / all-gather results are replicated)
     t = torch.tensor([worst], dtype=torch.float64)
     lo, hi = t.clone(), t.clone()
