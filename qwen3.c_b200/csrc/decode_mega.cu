@@ -1406,8 +1406,13 @@ int qw_mega_init(QwenCudaCtx* c) {
     const int fixed = ((xq_b + 127) & ~127) + ((scr_b + 127) & ~127) + ((misc_b + 127) & ~127) + ((bar_b + 127) & ~127)
                       + ((xres_b + 127) & ~127);
     const int avail = dev_smem - fixed - 1024; // 1 KB left for static shared + driver reserve
-    st->nslot = std::min(kMaxSlots, avail / kSlotBytes);
-    if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(st->nslot, atoi(e)));
+    // Ring depth: 5 slots by default although 7 fit. Measured on B200 (decode at context 4096): 4B shape 1.877 / 1.865 /
+    // 1.826 / 1.886 ms per token with 7 / 6 / 5 / 4 slots, 8B shape 2.459 (7) vs 2.426 (5): fewer bulk copies in flight per
+    // SM shorten every hand-off (scripts/ubench/handoff.cu: 13 us at 6 x 28 KB in flight, 3.3 us at 2) by more than the
+    // shallower prefetch costs. QWEN_MEGA_NSLOT overrides (up to what fits).
+    const int fit = std::min(kMaxSlots, avail / kSlotBytes);
+    st->nslot = std::min(fit, 5);
+    if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(fit, atoi(e)));
     if (const char* e = getenv("QWEN_MEGA_MODE")) st->dbg_mode = atoi(e);
     if (const char* e = getenv("QWEN_MEGA_L2AHEAD")) st->l2_ahead = std::max(0, atoi(e));
     if (getenv("QWEN_MEGA_VERBOSE")) fprintf(stderr, "[mega] nslot %d mode %d smem %d\n", st->nslot, st->dbg_mode, fixed);
