@@ -150,6 +150,15 @@ int qwen_cuda_debug_read(QwenCudaCtx* ctx, const char* what, void* host, size_t 
 int qwen_cuda_debug_quantize_fused(int8_t* q, float* s, const float* x, int n);
 /* Debug: run only the first n layers of the step (then final norm + classifier); -1 = all. */
 int qwen_cuda_debug_set_layers(QwenCudaCtx* ctx, int n);
+/* Debug (layer-by-layer parity with teacher forcing): the next steps run layers [l0, l1) only (l1 = -1: to the last),
+ * then the final norm and the classifier; x_host (dim floats, may be NULL) replaces the embedding row as the residual
+ * stream entering layer l0. (0, -1, NULL) restores the normal step. Both decode paths honour it. */
+int qwen_cuda_debug_set_window(QwenCudaCtx* ctx, int l0, int l1, const float* x_host);
+/* Debug (flip audit): record the Q8_0 activation vector (codes + scales) the persistent kernel feeds to every GEMV of the
+ * following steps. which = 4 * layer + {0: wq|wk|wv input, 1: wo input, 2: w1/w3 input, 3: w2 input}; 4 * n_layers = the
+ * classifier's input. read unpacks n codes and n / 64 scales of the last step (n = the GEMV's column count). */
+int qwen_cuda_debug_codes_enable(QwenCudaCtx* ctx, int on);
+int qwen_cuda_debug_codes_read(QwenCudaCtx* ctx, int which, int8_t* q, float* s, int n);
 /* Debug: per-CTA phase timestamps (globaltimer ns) of the persistent kernel, [grid][L+1][16].
  * enable returns the element count; read returns the grid size. */
 /* Debug: per-tile stamps of CTA 0 ([4][8192]: producer issue, consumer wait begin/end, done) for one

@@ -68,6 +68,9 @@ class _OrcModel(C.Structure):
            ("trace_on", C.c_int), ("tr_qkv_in_q", c_int8_p)]
         + [(n, c_float_p) for n in ("tr_qkv_in_s", "tr_q_rot", "tr_att_out", "tr_x_after_att",
                                     "tr_x_after_ffn", "tr_h")]
+        + [("tr_wo_in_q", c_int8_p), ("tr_wo_in_s", c_float_p), ("tr_ffn_in_q", c_int8_p), ("tr_ffn_in_s", c_float_p),
+           ("tr_w2_in_q", c_int8_p), ("tr_w2_in_s", c_float_p), ("tr_cls_in_q", c_int8_p), ("tr_cls_in_s", c_float_p),
+           ("tr_x_final", c_float_p), ("tr_x_normed", c_float_p)]
     )
 
 
@@ -218,6 +221,16 @@ class OracleModel:
             "x_after_att": self._arr(p.tr_x_after_att, L * D).reshape(L, D),
             "x_after_ffn": self._arr(p.tr_x_after_ffn, L * D).reshape(L, D),
             "h": self._arr(p.tr_h, L * Hd).reshape(L, Hd),
+            "wo_in_q": np.ctypeslib.as_array(p.tr_wo_in_q, shape=(L * P,)).copy().reshape(L, P),
+            "wo_in_s": self._arr(p.tr_wo_in_s, L * (P // p.group_size)).reshape(L, -1),
+            "ffn_in_q": np.ctypeslib.as_array(p.tr_ffn_in_q, shape=(L * D,)).copy().reshape(L, D),
+            "ffn_in_s": self._arr(p.tr_ffn_in_s, L * (D // p.group_size)).reshape(L, -1),
+            "w2_in_q": np.ctypeslib.as_array(p.tr_w2_in_q, shape=(L * Hd,)).copy().reshape(L, Hd),
+            "w2_in_s": self._arr(p.tr_w2_in_s, L * (Hd // p.group_size)).reshape(L, -1),
+            "cls_in_q": np.ctypeslib.as_array(p.tr_cls_in_q, shape=(D,)).copy(),
+            "cls_in_s": self._arr(p.tr_cls_in_s, D // p.group_size),
+            "x_final": self._arr(p.tr_x_final, D),
+            "x_normed": self._arr(p.tr_x_normed, D),
         }
 
     def close(self):

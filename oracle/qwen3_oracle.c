@@ -1,7 +1,8 @@
 /*
  * qwen3_oracle.c -- CPU restatement of qwen3.c's Q8_0 forward path.
  *
- * TEST INFRASTRUCTURE ONLY (see qwen3_oracle.h). Strictly serial, IEEE fp32.
+ * TEST INFRASTRUCTURE ONLY (see qwen3_oracle.h). IEEE fp32, every output element computed serially in the reference's
+ * order (the independent output rows of orc_matmul may run on several host threads: bit-identical, pinned).
  * Build: gcc -std=gnu17 -O2 -ffp-contract=off -fPIC -shared (oracle/Makefile).
  * Every function names the reference lines it restates; arithmetic order and
  * association are kept exactly so results are bit-identical to the reference's
@@ -59,6 +60,10 @@ void orc_q8_dequantize(float* x, const int8_t* q, const float* s, int n, int gs)
  * GPU's per-group dots can be compared bit for bit. */
 void orc_group_dots(int32_t* dots, const int8_t* xq, const int8_t* wq, int n, int d, int gs) {
     const int groups = n / gs;
+    /* Output rows are independent: they may run on several host threads (the checker must finish the 1.7B / 4B
+     * shapes in seconds per token). Inside a row everything is the reference's serial arithmetic, so the result is
+     * bit-identical to the single-thread run whatever the thread count (pinned in tests/test_oracle_pinned.py). */
+#pragma omp parallel for schedule(static) if ((size_t) d * (size_t) n > (size_t) 1 << 18)
     for (int i = 0; i < d; ++i) {
         const int8_t* row = wq + (size_t) i * n;
         for (int g = 0; g < groups; ++g) {
@@ -320,6 +325,8 @@ void orc_model_close(OrcModel* m) {
     free(m->aq); free(m->as);
     free(m->tr_qkv_in_q); free(m->tr_qkv_in_s); free(m->tr_q_rot); free(m->tr_att_out);
     free(m->tr_x_after_att); free(m->tr_x_after_ffn); free(m->tr_h);
+    free(m->tr_wo_in_q); free(m->tr_wo_in_s); free(m->tr_ffn_in_q); free(m->tr_ffn_in_s); free(m->tr_w2_in_q);
+    free(m->tr_w2_in_s); free(m->tr_cls_in_q); free(m->tr_cls_in_s); free(m->tr_x_final); free(m->tr_x_normed);
     if (m->map) {
         munmap(m->map, m->map_len);
     }
@@ -336,8 +343,21 @@ int orc_trace_enable(OrcModel* m) {
     m->tr_x_after_att = (float*) calloc(L * D, sizeof(float));
     m->tr_x_after_ffn = (float*) calloc(L * D, sizeof(float));
     m->tr_h = (float*) calloc(L * Hd, sizeof(float));
+    const size_t gs = (size_t) m->group_size;
+    m->tr_wo_in_q = (int8_t*) calloc(L * P, 1);
+    m->tr_wo_in_s = (float*) calloc(L * (P / gs), sizeof(float));
+    m->tr_ffn_in_q = (int8_t*) calloc(L * D, 1);
+    m->tr_ffn_in_s = (float*) calloc(L * (D / gs), sizeof(float));
+    m->tr_w2_in_q = (int8_t*) calloc(L * Hd, 1);
+    m->tr_w2_in_s = (float*) calloc(L * (Hd / gs), sizeof(float));
+    m->tr_cls_in_q = (int8_t*) calloc(D, 1);
+    m->tr_cls_in_s = (float*) calloc(D / gs, sizeof(float));
+    m->tr_x_final = (float*) calloc(D, sizeof(float));
+    m->tr_x_normed = (float*) calloc(D, sizeof(float));
     m->trace_on = m->tr_qkv_in_q && m->tr_qkv_in_s && m->tr_q_rot && m->tr_att_out
-                  && m->tr_x_after_att && m->tr_x_after_ffn && m->tr_h;
+                  && m->tr_x_after_att && m->tr_x_after_ffn && m->tr_h && m->tr_wo_in_q && m->tr_wo_in_s
+                  && m->tr_ffn_in_q && m->tr_ffn_in_s && m->tr_w2_in_q && m->tr_w2_in_s && m->tr_cls_in_q
+                  && m->tr_cls_in_s && m->tr_x_final && m->tr_x_normed;
     return m->trace_on ? 0 : -1;
 }
 
@@ -392,6 +412,10 @@ float* orc_forward(OrcModel* m, int token, int pos) {
         }
 
         orc_q8_quantize(m->aq, m->as, m->xb, P, gs);                      /* :291 */
+        if (m->trace_on) {
+            memcpy(m->tr_wo_in_q + (size_t) l * P, m->aq, (size_t) P);
+            memcpy(m->tr_wo_in_s + (size_t) l * (P / gs), m->as, sizeof(float) * (size_t) (P / gs));
+        }
         orc_matmul(m->xb, m->aq, m->as, m->wo[l].q, m->wo[l].s, P, D, gs);/* :292-294 */
         for (int i = 0; i < D; ++i) {                                     /* :295-298 */
             m->x[i] += m->xb[i];
@@ -402,6 +426,10 @@ float* orc_forward(OrcModel* m, int token, int pos) {
 
         orc_rmsnorm(m->xb, m->x, m->ffn_norm + (size_t) l * D, D);        /* :303 */
         orc_q8_quantize(m->aq, m->as, m->xb, D, gs);                      /* :308 */
+        if (m->trace_on) {
+            memcpy(m->tr_ffn_in_q + (size_t) l * D, m->aq, (size_t) D);
+            memcpy(m->tr_ffn_in_s + (size_t) l * (D / gs), m->as, sizeof(float) * (size_t) (D / gs));
+        }
         orc_matmul(m->h1, m->aq, m->as, m->w1[l].q, m->w1[l].s, D, Hd, gs); /* :309-311 */
         orc_matmul(m->h3, m->aq, m->as, m->w3[l].q, m->w3[l].s, D, Hd, gs); /* :312-314 */
         orc_swiglu(m->h1, m->h3, Hd);                                     /* :319-321 */
@@ -409,6 +437,10 @@ float* orc_forward(OrcModel* m, int token, int pos) {
             memcpy(m->tr_h + (size_t) l * Hd, m->h1, sizeof(float) * (size_t) Hd);
         }
         orc_q8_quantize(m->aq, m->as, m->h1, Hd, gs);                     /* :326 */
+        if (m->trace_on) {
+            memcpy(m->tr_w2_in_q + (size_t) l * Hd, m->aq, (size_t) Hd);
+            memcpy(m->tr_w2_in_s + (size_t) l * (Hd / gs), m->as, sizeof(float) * (size_t) (Hd / gs));
+        }
         orc_matmul(m->xb, m->aq, m->as, m->w2[l].q, m->w2[l].s, Hd, D, gs); /* :327-334 */
         for (int i = 0; i < D; ++i) {                                     /* :335-338 */
             m->x[i] += m->xb[i];
@@ -418,8 +450,16 @@ float* orc_forward(OrcModel* m, int token, int pos) {
         }
     }
 
+    if (m->trace_on) {
+        memcpy(m->tr_x_final, m->x, sizeof(float) * (size_t) D);
+    }
     orc_rmsnorm(m->x, m->x, m->out_norm, D);                              /* :344 */
     orc_q8_quantize(m->aq, m->as, m->x, D, gs);                           /* :347 */
+    if (m->trace_on) {
+        memcpy(m->tr_x_normed, m->x, sizeof(float) * (size_t) D);
+        memcpy(m->tr_cls_in_q, m->aq, (size_t) D);
+        memcpy(m->tr_cls_in_s, m->as, sizeof(float) * (size_t) (D / gs));
+    }
     orc_matmul(m->logits, m->aq, m->as, m->cls.q, m->cls.s, D, m->vocab_size, gs); /* :348 */
     return m->logits;
 }

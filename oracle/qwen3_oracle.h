@@ -80,6 +80,17 @@ typedef struct OrcModel {
     float* tr_x_after_att;/* [L][dim]   residual after wo */
     float* tr_x_after_ffn;/* [L][dim]   residual after w2 */
     float* tr_h;          /* [L][Hd]    swiglu output */
+    /* the other three quantised GEMV inputs of every layer, the classifier's, and the fp32 vectors they came from */
+    int8_t* tr_wo_in_q;   /* [L][P]     codes fed to wo */
+    float* tr_wo_in_s;    /* [L][P/gs] */
+    int8_t* tr_ffn_in_q;  /* [L][dim]   codes fed to w1/w3 */
+    float* tr_ffn_in_s;   /* [L][dim/gs] */
+    int8_t* tr_w2_in_q;   /* [L][Hd]    codes fed to w2 */
+    float* tr_w2_in_s;    /* [L][Hd/gs] */
+    int8_t* tr_cls_in_q;  /* [dim]      codes fed to the classifier */
+    float* tr_cls_in_s;   /* [dim/gs] */
+    float* tr_x_final;    /* [dim]      residual stream entering the final norm */
+    float* tr_x_normed;   /* [dim]      after the final norm (what the classifier's quantiser sees) */
 } OrcModel;
 
 OrcModel* orc_model_open(const char* path, int seq_len_override);

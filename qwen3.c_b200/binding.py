@@ -109,6 +109,9 @@ class QwenLib:
         L.qwen_cuda_kv_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_kv_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         L.qwen_cuda_debug_set_layers.argtypes = [C.c_void_p, C.c_int]
+        L.qwen_cuda_debug_set_window.argtypes = [C.c_void_p, C.c_int, C.c_int, c_float_p]
+        L.qwen_cuda_debug_codes_enable.argtypes = [C.c_void_p, C.c_int]
+        L.qwen_cuda_debug_codes_read.argtypes = [C.c_void_p, C.c_int, c_int8_p, c_float_p, C.c_int]
         L.qwen_cuda_debug_quantize_fused.argtypes = [c_int8_p, c_float_p, c_float_p, C.c_int]
         L.qwen_cuda_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
         L.qwen_cuda_matmul_group_dots.argtypes = [c_int32_p, c_int8_p, c_int8_p, C.c_int, C.c_int, C.c_int]
@@ -264,6 +267,26 @@ class B200Model:
 
     def set_layers(self, n: int):
         self.ql._ok(self.ql.lib.qwen_cuda_debug_set_layers(self.ctx, n), "set_layers")
+
+    def set_window(self, l0: int = 0, l1: int = -1, x=None):
+        """Debug: the next steps run layers [l0, l1) only; x (dim floats) replaces the embedding row entering layer l0."""
+        xp = None
+        if x is not None:
+            x = np.ascontiguousarray(x, np.float32)
+            assert x.size == self.p.dim
+            xp = _fp(x)
+        self.ql._ok(self.ql.lib.qwen_cuda_debug_set_window(self.ctx, l0, l1, xp), "set_window")
+
+    def codes_enable(self, on: bool = True):
+        self.ql._ok(self.ql.lib.qwen_cuda_debug_codes_enable(self.ctx, int(on)), "codes_enable")
+
+    def codes_read(self, which: int, n: int):
+        """Q8_0 codes + scales the persistent kernel fed to GEMV `which` (4 * layer + {0 qkv, 1 wo, 2 w1/w3, 3 w2};
+        4 * n_layers = classifier) in the last step."""
+        q = np.zeros(n, np.int8)
+        sc = np.zeros(n // 64, np.float32)
+        self.ql._ok(self.ql.lib.qwen_cuda_debug_codes_read(self.ctx, which, q.ctypes.data_as(c_int8_p), _fp(sc), n), "codes_read")
+        return q, sc
 
     def decode_greedy(self, first_token: int, pos0: int, n: int) -> np.ndarray:
         out = np.zeros(n, np.int32)

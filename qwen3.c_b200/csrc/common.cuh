@@ -161,6 +161,11 @@ struct QwenCudaCtx {
     void* mega;       // persistent-kernel state (decode_mega.cu)
     void* prefill;    // prefill activation buffers (prefill.cu), allocated on first use
     int layers_run;   // debug: run only the first n layers (-1 = all)
+    int layer_begin;  // debug: first layer to run (0)
+    float* x_inject;  // debug: [D] residual stream entering layer_begin instead of the embedding row
+    int x_inject_on;
+    uint8_t* dbg_codes; // debug: [4 * L + 1][dbg_codes_stride] Q8_0 activation vectors of the last persistent-kernel step (SG layout)
+    size_t dbg_codes_stride;
     float* logits_pinned; // optional pinned bounce buffer
     float* sample_ws;     // workspace of the device sampler (sampler.cu), allocated on first use
     size_t bytes_weights, bytes_kv;

@@ -213,6 +213,8 @@ extern "C" void qwen_cuda_destroy(QwenCudaCtx* c) {
     qw_tp_free(c);
     if (c->logits_all) cudaFree(c->logits_all);
     if (c->sample_ws) cudaFree(c->sample_ws);
+    if (c->x_inject) cudaFree(c->x_inject);
+    if (c->dbg_codes) cudaFree(c->dbg_codes);
     if (c->w_emb != c->w_cls) cudaFree(c->w_emb);
     void* bufs[] = {c->w_qkv, c->w_o, c->w_13, c->w_2, c->w_cls, c->att_norm, c->ffn_norm, c->out_norm, c->q_norm,
                     c->k_norm, c->rope_cos, c->rope_sin, c->k_cache, c->v_cache, c->x, c->xb, c->qkv, c->q, c->att,
@@ -284,6 +286,56 @@ extern "C" int qwen_cuda_debug_quantize_fused(int8_t* q, float* s, const float* 
 extern "C" int qwen_cuda_debug_set_layers(QwenCudaCtx* c, int n) {
     if (!c) return -2;
     c->layers_run = n;
+    return 0;
+}
+
+// Debug (layer-by-layer parity with teacher forcing): the next steps run layers [l0, l1) only, then the final norm and the
+// classifier; x_host (dim floats) replaces the embedding row as the residual stream entering layer l0. Both paths.
+extern "C" int qwen_cuda_debug_set_window(QwenCudaCtx* c, int l0, int l1, const float* x_host) {
+    if (!c || l0 < 0 || l0 > c->L || (l1 >= 0 && l1 < l0) || l1 > c->L) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    c->layer_begin = l0;
+    c->layers_run = l1;
+    c->x_inject_on = 0;
+    if (x_host) {
+        if (!c->x_inject) QW_CUDA(cudaMalloc((void**) &c->x_inject, (size_t) qw_pad_cols(c->D) * 4));
+        QW_CUDA(cudaMemcpy(c->x_inject, x_host, (size_t) c->D * 4, cudaMemcpyHostToDevice));
+        c->x_inject_on = 1;
+    }
+    return 0;
+}
+
+// Debug (flip audit): record the Q8_0 activation vector -- codes and scales -- the persistent kernel feeds to every GEMV of
+// the following steps. Vector `which` = 4 * layer + {0: wq|wk|wv input, 1: wo input, 2: w1/w3 input, 3: w2 input},
+// 4 * n_layers: classifier input. read unpacks n codes and n / 64 scales of the last step.
+extern "C" int qwen_cuda_debug_codes_enable(QwenCudaCtx* c, int on) {
+    if (!c) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    if (!on) {
+        if (c->dbg_codes) cudaFree(c->dbg_codes);
+        c->dbg_codes = nullptr;
+        return 0;
+    }
+    if (!c->dbg_codes) {
+        c->dbg_codes_stride = qw_row_bytes(std::max(c->D, std::max(c->Pl, c->Hdl)));
+        QW_CUDA(cudaMalloc((void**) &c->dbg_codes, (size_t) (4 * c->L + 1) * c->dbg_codes_stride));
+        QW_CUDA(cudaMemset(c->dbg_codes, 0, (size_t) (4 * c->L + 1) * c->dbg_codes_stride));
+    }
+    return 0;
+}
+extern "C" int qwen_cuda_debug_codes_read(QwenCudaCtx* c, int which, int8_t* q, float* s, int n) {
+    if (!c || !c->dbg_codes || which < 0 || which > 4 * c->L || n <= 0 || n % 64 || qw_row_bytes(n) > c->dbg_codes_stride) return -2;
+    QW_CUDA(cudaSetDevice(c->device));
+    QW_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<uint8_t> h(qw_row_bytes(n));
+    QW_CUDA(cudaMemcpy(h.data(), c->dbg_codes + (size_t) which * c->dbg_codes_stride, h.size(), cudaMemcpyDeviceToHost));
+    for (int g = 0; g < n / 64; ++g) {
+        const uint8_t* rec = h.data() + (size_t) (g >> 2) * QW_SG_BYTES;
+        memcpy(q + (size_t) g * 64, rec + (g & 3) * 64, 64);
+        memcpy(s + g, rec + 256 + (g & 3) * 4, 4);
+    }
     return 0;
 }
 

@@ -81,8 +81,13 @@ struct MatDesc {
 struct MegaParams {
     int D, Hdl, L, Hl, KVHl, Pl, Kl, Vl, S, kv_mul;
     int pos, token, layers_run;
+    int l_begin;             // debug: first layer to run (0 normally); the residual stream then starts from x_inject
+    const float* x_inject;   // debug: replaces the embedding row as x entering layer l_begin (nullptr normally)
+    uint8_t* dbg_codes;      // debug: CTA 0 copies the Q8_0 activation vector of every GEMV here, [4 * L + 1][dbg_stride]
+    int dbg_stride;
     int perm;       // CTA -> row-block permutation multiplier (coprime to the grid)
     int dbg_mode;   // 0 normal; 1 consumers skip the GEMV math (ring throughput test)
+    int inflight;   // producer: at most this many bulk-copy tiles in flight per SM (0 = the ring depth)
     int l2_ahead;   // 0: no L2 prefetch; else prefetch the next sub-phase (and this many 32 KB pieces of the classifier)
     const int* token_dev;
     MatDesc mat[5]; // 0 wq|wk|wv, 1 wo, 2 w1/w3 interleaved, 3 w2, 4 classifier
@@ -113,7 +118,7 @@ struct MegaState {
     int o_xa = 0, o_xb = 0, o_qkv = 0, o_h = 0, o_attq = 0, o_part = 0, part_slots = 0;
     unsigned launches = 0;
     int last_layers = 0;
-    int grid = 0, nslot = 0, dbg_mode = 0, perm = 1, l2_ahead = 0;
+    int grid = 0, nslot = 0, dbg_mode = 0, perm = 1, l2_ahead = 0, inflight = 0;
     unsigned long long* prof = nullptr;
     size_t smem = 0;
     int off_xq, off_scr, off_misc, off_bar, off_xres = 0;
@@ -132,6 +137,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) { // `count` arrivals at once
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -392,12 +400,23 @@ __device__ __noinline__ void prefetch_subphase(const MegaParams& p, int sp) {
 // does, but a bulk copy that hits L2 is no faster than one that streams from HBM -- 148 SMs x 6 copies of
 // 28 KB in flight top out at 7.5 TB/s either way -- so the ring refills no sooner and the step time does
 // not improve (2.07 ms vs 2.14 ms with the prefetch on).
+// Optional cap on the bulk copies in flight (QWEN_MEGA_INFLIGHT): before issuing tile i the producer waits until tile
+// i - cap has landed. A full ring's worth of copies issued at once at every phase boundary (5 x 28 KB x 148 SMs = 20 MB)
+// keeps the L2 miss queues full for ~3 us, and the hand-off polls of that moment queue behind them.
+__device__ __forceinline__ void producer_throttle(const Shared& sh, const MegaParams& p, const RingPos& rp, unsigned issued) {
+    if (p.inflight <= 0 || issued < (unsigned) p.inflight) return;
+    const unsigned back = (unsigned) p.inflight;
+    const unsigned slot = rp.slot >= back ? rp.slot - back : rp.slot + (unsigned) p.nslot - back;
+    const unsigned par = rp.slot >= back ? rp.par : rp.par ^ 1u;
+    mbar_wait(sh, p, sh.full + slot * 8, par, 5);
+}
 __device__ void producer(const Shared& sh, const MegaParams& p) {
     RingPos rp{0u, 0u};
     const int nph = 4 * p.layers_run;
     int sp = 0;
+    unsigned issued = 0;
 #pragma unroll 1
-    for (int ph = 0; ph <= nph; ++ph) {
+    for (int ph = 4 * p.l_begin; ph <= nph; ++ph) {
         const int l = ph >> 2, k = ph == nph ? 4 : (ph & 3);
         if (k == 1) { // the layer's KV tiles come between QKV and WO
             if (p.l2_ahead) prefetch_subphase(p, sp + 1);
@@ -408,6 +427,7 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
                 const int cnt = min(kChunk, a.p_hi - p0);
                 const unsigned slot = rp.slot, par = rp.par;
                 mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 2);
+                producer_throttle(sh, p, rp, issued++);
                 const size_t off = (((size_t) l * p.KVHl + a.kvh) * p.S + p0) * 128;
                 const uint32_t bytes = (uint32_t) cnt * 512u;
                 const uint32_t dst = smem_u32(sh.ring + (size_t) slot * kSlotBytes);
@@ -428,6 +448,7 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
             const int nr = min(m.rt, r1 - r);
             const unsigned slot = rp.slot, par = rp.par;
             mbar_wait(sh, p, sh.empty + slot * 8, par ^ 1, 1);
+            producer_throttle(sh, p, rp, issued++);
             const uint32_t bytes = (uint32_t) (nr * rb);
             mbar_expect_tx(sh.full + slot * 8, bytes);
             bulk_g2s(smem_u32(sh.ring + (size_t) slot * kSlotBytes), base + (size_t) r * rb, bytes, sh.full + slot * 8);
@@ -452,6 +473,45 @@ __device__ void producer(const Shared& sh, const MegaParams& p) {
 // of the unit into slot tp_rank of rank q's arena at BYTE offset `out` (st.relaxed.sys over NVLink; the
 // own rank is one of the q). That IS the all-reduce: the readers add the tp slots in rank order (prologue_quant).
 // `out` is a flow-arena vector (or the logits): each element is stored exactly once.
+// one Q8_0 group (64 codes + scale at group index G of the record layout) of TWO weight rows against the activation
+// vector: two dp4a chains of 8 per row (dp4a: ~24 cycles dependent latency), then ((float) dot * ws) * xs (forward.c:94-96)
+__device__ __forceinline__ void gemv_step2(const uint8_t* xq, const uint8_t* rowa, const uint8_t* rowb, int G, int rot, float& acca, float& accb) {
+    const int off = (G >> 2) * QW_SG_BYTES + (G & 3) * 64;
+    int da0 = 0, da1 = 0, db0 = 0, db1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pc = ((i + rot) & 3) * 16;
+        const int4 x = *reinterpret_cast<const int4*>(xq + off + pc);
+        const int4 a = *reinterpret_cast<const int4*>(rowa + off + pc);
+        const int4 b = *reinterpret_cast<const int4*>(rowb + off + pc);
+        if (i < 2) {
+            da0 = __dp4a(a.x, x.x, da0); db0 = __dp4a(b.x, x.x, db0); da0 = __dp4a(a.y, x.y, da0); db0 = __dp4a(b.y, x.y, db0);
+            da0 = __dp4a(a.z, x.z, da0); db0 = __dp4a(b.z, x.z, db0); da0 = __dp4a(a.w, x.w, da0); db0 = __dp4a(b.w, x.w, db0);
+        } else {
+            da1 = __dp4a(a.x, x.x, da1); db1 = __dp4a(b.x, x.x, db1); da1 = __dp4a(a.y, x.y, da1); db1 = __dp4a(b.y, x.y, db1);
+            da1 = __dp4a(a.z, x.z, da1); db1 = __dp4a(b.z, x.z, db1); da1 = __dp4a(a.w, x.w, da1); db1 = __dp4a(b.w, x.w, db1);
+        }
+    }
+    const int so = (G >> 2) * QW_SG_BYTES + 256 + (G & 3) * 4;
+    const float xs = *reinterpret_cast<const float*>(xq + so);
+    acca = __fadd_rn(acca, q8_term(da0 + da1, *reinterpret_cast<const float*>(rowa + so), xs));
+    accb = __fadd_rn(accb, q8_term(db0 + db1, *reinterpret_cast<const float*>(rowb + so), xs));
+}
+// the same for ONE row: four chains of 4
+__device__ __forceinline__ float gemv_step1(const uint8_t* xq, const uint8_t* row, int G, int rot) {
+    const int off = (G >> 2) * QW_SG_BYTES + (G & 3) * 64;
+    int d[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pc = ((i + rot) & 3) * 16;
+        const int4 x = *reinterpret_cast<const int4*>(xq + off + pc);
+        const int4 a = *reinterpret_cast<const int4*>(row + off + pc);
+        d[i] = __dp4a(a.x, x.x, d[i]); d[i] = __dp4a(a.y, x.y, d[i]); d[i] = __dp4a(a.z, x.z, d[i]); d[i] = __dp4a(a.w, x.w, d[i]);
+    }
+    const int so = (G >> 2) * QW_SG_BYTES + 256 + (G & 3) * 4;
+    return q8_term((d[0] + d[1]) + (d[2] + d[3]), *reinterpret_cast<const float*>(row + so), *reinterpret_cast<const float*>(xq + so));
+}
+
 template <bool TP>
 __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& p, const MatDesc& m, int /*layer*/, RingPos& rp, float* out, const float* resid) {
     int r0, r1;
@@ -463,6 +523,11 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     const int groups = sgpr * 4; // padded groups carry zero codes and zero scales: they add +0
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rot = (lane & 2);
+    // column split of a row over the lanes: nfull steps of 32 groups (lane = group), then a tail of rem groups
+    const int nfull = groups >> 5, rem = groups & 31;
+    const bool tail_split = rem > 0 && rem <= 16;
+    const bool t_rowb = tail_split && lane >= rem;
+    const int tG = rem == 0 ? -1 : tail_split ? (lane < 2 * rem ? nfull * 32 + (t_rowb ? lane - rem : lane) : -1) : (lane < rem ? nfull * 32 + lane : -1);
     const int nrows = r1 - r0;
     const int upt = (rt + 1) / 2;             // units per tile (rt is 1 only when a row fills the slot)
     const int rows_pu = rt >= 2 ? 2 : 1;      // rows per unit
@@ -470,12 +535,32 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     const bool staged = m.stage != 0;
     float* stage = sh.scr;                    // free during the GEMV phases (attention / combine scratch)
     int u = warp; // this warp's next unit
+    float pa0 = 0.0f, pb0 = 0.0f, xres = 0.0f; // lane partials of a unit whose reduction waits for the next unit
+    int grow0 = 0;
+    bool two0 = false, pend = false;
+#ifdef QW_UNITPROF
+    long long up_wait = 0, up_math = 0, up_epi = 0, up_units = 0, up_t, up_bar = 0, up_store = 0;
+    const long long up_entry = clock64();
+#define UP_BEGIN() up_t = clock64()
+#define UP_END(acc) do { const long long up_n = clock64(); acc += up_n - up_t; up_t = up_n; } while (0)
+#else
+#define UP_BEGIN()
+#define UP_END(acc)
+#endif
 #pragma unroll 1
     for (int t0 = 0; t0 < total; t0 += upt, rp.next(p.nslot)) {
-        const unsigned slot = rp.slot, par = rp.par;
-        mbar_wait(sh, p, sh.full + slot * 8, par, 3);
-        const uint8_t* tile = sh.ring + (size_t) slot * kSlotBytes;
         const int t1 = min(t0 + upt, total);
+        // Only the warps that own a unit of the tile touch it (measured: walking a tile -- wait, __syncwarp, arrive -- cost a
+        // warp ~400 cycles, and with 5 units per tile two thirds of a warp's tile visits were for nothing: 28 % of the
+        // w1/w3 phase). The slot's `empty` barrier still counts 15 arrivals: the owner of the tile's first unit brings the
+        // arrivals of the warps that have no unit here.
+        if (u >= t1) continue;
+        const unsigned slot = rp.slot, par = rp.par;
+        const uint32_t arrivals = u == t0 ? (uint32_t) (kConsumerWarps + 1 - min(t1 - t0, kConsumerWarps)) : 1u;
+        UP_BEGIN();
+        mbar_wait(sh, p, sh.full + slot * 8, par, 3);
+        UP_END(up_wait);
+        const uint8_t* tile = sh.ring + (size_t) slot * kSlotBytes;
         bool released = false;
         if (p.dbg_mode >= 1) // ring throughput test: skip the math
             while (u < t1) u += kConsumerWarps;
@@ -486,16 +571,17 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
             const bool two = rows_pu == 2 && grow + 1 < r1;
             const uint8_t* rowa = tile + (size_t) lr * rb;
             const uint8_t* rowb = two ? rowa + rb : rowa;
-            float xres = 0.0f;
-            if (KIND == 1 && lane < 2 && (lane == 0 || two)) // issued early: hides the L2 round trip
-                xres = __uint_as_float(ldf_u32(resid + grow + lane));
+            // residual element of the row this lane will store (see the epilogue): lane 16 * (unit of the pair) + 8 * (row
+            // of the unit); issued early, it hides the L2 round trip
+            if (KIND == 1 && (lane & 7) == 0 && ((lane & 16) != 0) == pend && ((lane & 8) == 0 || two))
+                xres = __uint_as_float(ldf_u32(resid + grow + ((lane >> 3) & 1)));
             float acca = 0.0f, accb = 0.0f;
+            int s = 0;
 #pragma unroll 1
-            for (int G = lane; G < groups; G += 64) {
-                const int G2 = G + 32;
-                const bool has2 = G2 < groups;
+            for (; s + 2 <= nfull; s += 2) { // two full 32-group steps at a time: four dp4a chains of 16
+                const int G = s * 32 + lane, G2 = G + 32;
                 const int off = (G >> 2) * QW_SG_BYTES + (G & 3) * 64;
-                const int off2 = has2 ? (G2 >> 2) * QW_SG_BYTES + (G2 & 3) * 64 : off;
+                const int off2 = (G2 >> 2) * QW_SG_BYTES + (G2 & 3) * 64;
                 int da0 = 0, da1 = 0, db0 = 0, db1 = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -512,54 +598,92 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
                     da0 = __dp4a(a0.w, x0.w, da0); da1 = __dp4a(a1.w, x1.w, da1); db0 = __dp4a(b0.w, x0.w, db0); db1 = __dp4a(b1.w, x1.w, db1);
                 }
                 const int so = (G >> 2) * QW_SG_BYTES + 256 + (G & 3) * 4;
+                const int so2 = (G2 >> 2) * QW_SG_BYTES + 256 + (G2 & 3) * 4;
                 const float xs0 = *reinterpret_cast<const float*>(sh.xq + so);
+                const float xs1 = *reinterpret_cast<const float*>(sh.xq + so2);
                 acca = __fadd_rn(acca, q8_term(da0, *reinterpret_cast<const float*>(rowa + so), xs0));
                 accb = __fadd_rn(accb, q8_term(db0, *reinterpret_cast<const float*>(rowb + so), xs0));
-                if (has2) {
-                    const int so2 = (G2 >> 2) * QW_SG_BYTES + 256 + (G2 & 3) * 4;
-                    const float xs1 = *reinterpret_cast<const float*>(sh.xq + so2);
-                    acca = __fadd_rn(acca, q8_term(da1, *reinterpret_cast<const float*>(rowa + so2), xs1));
-                    accb = __fadd_rn(accb, q8_term(db1, *reinterpret_cast<const float*>(rowb + so2), xs1));
-                }
+                acca = __fadd_rn(acca, q8_term(da1, *reinterpret_cast<const float*>(rowa + so2), xs1));
+                accb = __fadd_rn(accb, q8_term(db1, *reinterpret_cast<const float*>(rowb + so2), xs1));
             }
+            // an odd full step, then the tail of rem < 32 groups when more than 16 lanes have one: one group per lane for
+            // both rows (real branches: lanes without a group issue no shared-memory wavefronts; one copy of the code)
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                const int G = k == 0 ? (s < nfull ? s * 32 + lane : -1) : (tail_split ? -1 : tG);
+                if (G >= 0) gemv_step2(sh.xq, rowa, rowb, G, rot, acca, accb);
+            }
+            // a tail of <= 16 groups: lane l < rem takes the group for row a, lane rem + l for row b (n = 2560: 8 + 8 lanes
+            // instead of a second full-width step of which 24 lanes only reloaded their first group: 37 % fewer wavefronts)
+            if (tail_split && tG >= 0) {
+                const float t = gemv_step1(sh.xq, t_rowb ? rowb : rowa, tG, rot);
+                if (t_rowb) accb = __fadd_rn(accb, t); else acca = __fadd_rn(acca, t);
+            }
+            UP_END(up_math);
             if (u + kConsumerWarps >= t1) {
                 // this warp's last unit in the tile: every byte it needs from the ring slot has been consumed by a
                 // dp4a, so the slot goes back to the producer BEFORE the cross-lane reduction and the epilogue
                 __syncwarp();
-                if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+                if (lane == 0) mbar_arrive_n(sh.empty + slot * 8, arrivals);
                 released = true;
             }
+            // Cross-lane reduction and epilogue, for TWO units (4 rows) at a time: the first unit's lane partials wait in
+            // registers (measured: the 10-shuffle tree + epilogue per unit cost 580-710 cycles against 1200 for the dot
+            // products). A transposing butterfly folds 4 values per lane in 6 shuffles: after xor 16 / xor 8 a lane keeps
+            // row 2 * (lane >> 4) + ((lane >> 3) & 1), after xor 4, 2, 1 all 8 lanes of that row's group hold its sum.
+            const bool last_unit = u + kConsumerWarps >= total;
+            if (!pend && !last_unit) {
+                pa0 = acca; pb0 = accb; grow0 = grow; two0 = two;
+                pend = true;
+            } else {
+                // rows: 0, 1 = the pending unit (or this one when nothing is pending), 2, 3 = this unit after a pending one
+                const float v0 = pend ? pa0 : acca, v1 = pend ? pb0 : accb, v2 = pend ? acca : 0.0f, v3 = pend ? accb : 0.0f;
+                const bool hi = (lane & 16) != 0, mid = (lane & 8) != 0;
+                float t0 = __fadd_rn(hi ? v2 : v0, __shfl_xor_sync(0xffffffffu, hi ? v0 : v2, 16));
+                float t1 = __fadd_rn(hi ? v3 : v1, __shfl_xor_sync(0xffffffffu, hi ? v1 : v3, 16));
+                float r = __fadd_rn(mid ? t1 : t0, __shfl_xor_sync(0xffffffffu, mid ? t0 : t1, 8));
+                r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+                r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+                r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+                // this lane's row: unit `hi` of the pair (0 = the older one), row `mid` of the unit
+                const int ug = (pend && !hi) ? grow0 : grow;              // first row of the lane's unit
+                const bool utwo = (pend && !hi) ? two0 : two;
+                const bool live = (!hi || pend) && (!mid || utwo);        // the lane's row exists
+                if (KIND == 2) {
+                    const float gate = __shfl_xor_sync(0xffffffffu, r, 8); // the w3 row of the pair sits 8 lanes up
+                    if ((lane & 15) == 0 && live) {
+                        const float hv = __fmul_rn(silu_ref(r), gate);
+                        if (staged) stage[(ug - r0) >> 1] = hv; else stf_f32(out + (ug >> 1), hv);
+                    }
+                } else if (TP && KIND == 3 && staged) {
+                    if ((lane & 7) == 0 && live) stage[ug + (mid ? 1 : 0) - r0] = r;
+                } else if (TP && KIND == 3) {
+                    if ((lane & 7) < p.tp && live) { // lane q of the row's group of 8 stores to rank q
+                        char* base = reinterpret_cast<char*>(p.peer_flow[0]);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                acca = __fadd_rn(acca, __shfl_xor_sync(0xffffffffu, acca, o));
-                accb = __fadd_rn(accb, __shfl_xor_sync(0xffffffffu, accb, o));
-            }
-            if (KIND == 2) {
-                if (lane == 0) {
-                    const float hv = __fmul_rn(silu_ref(acca), accb);
-                    if (staged) stage[(grow - r0) >> 1] = hv; else stf_f32(out + (grow >> 1), hv);
+                        for (int q = 1; q < kMaxTp; ++q) // static indices: a dynamic one makes a local copy of the parameter array
+                            if ((lane & 7) == q) base = reinterpret_cast<char*>(p.peer_flow[q]);
+                        stf_sys_f32(reinterpret_cast<float*>(base + reinterpret_cast<size_t>(out)) + ug + (mid ? 1 : 0), r);
+                    }
+                } else if ((lane & 7) == 0 && live) {
+                    const float o = KIND == 1 ? __fadd_rn(xres, r) : r;
+                    if (staged) stage[ug + (mid ? 1 : 0) - r0] = o; else stf_f32(out + ug + (mid ? 1 : 0), o);
                 }
-            } else if (TP && KIND == 3 && staged) {
-                if (lane < 2 && (lane == 0 || two)) stage[grow + lane - r0] = lane == 0 ? acca : accb;
-            } else if (TP && KIND == 3) {
-                if (lane < 2 * p.tp && ((lane & 1) == 0 || two)) {
-                    char* base = reinterpret_cast<char*>(p.peer_flow[0]);
-#pragma unroll
-                    for (int q = 1; q < kMaxTp; ++q) // static indices: a dynamic one makes a local copy of the parameter array
-                        if ((lane >> 1) == q) base = reinterpret_cast<char*>(p.peer_flow[q]);
-                    stf_sys_f32(reinterpret_cast<float*>(base + reinterpret_cast<size_t>(out)) + grow + (lane & 1), (lane & 1) ? accb : acca);
-                }
-            } else if (lane < 2 && (lane == 0 || two)) {
-                const float v = lane == 0 ? acca : accb;
-                const float o = KIND == 1 ? __fadd_rn(xres, v) : v;
-                if (staged) stage[grow + lane - r0] = o; else stf_f32(out + grow + lane, o);
+                pend = false;
             }
+            UP_END(up_epi);
+#ifdef QW_UNITPROF
+            ++up_units;
+#endif
         }
-        if (!released) { // no unit of this warp in the tile
+        if (!released) { // debug mode 1 only (math skipped)
             __syncwarp();
-            if (lane == 0) mbar_arrive(sh.empty + slot * 8);
+            if (lane == 0) mbar_arrive_n(sh.empty + slot * 8, arrivals);
         }
     }
+#ifdef QW_UNITPROF
+    const long long up_loop_end = clock64();
+#endif
     // push this warp's results out NOW: without a fence the stores sit in the SM's write path for
     // microseconds (measured, scripts/ubench/handoff.cu: 2.7 us per hand-off without, 1.05 us with)
     if (staged) {
@@ -567,7 +691,9 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
         // thread sends them with a single TMA bulk store. The async proxy writes straight to L2 -- no SM store queue shared
         // with the polling loads, and no warp waits in a fence (13 % of all stall samples in ncu with per-warp stores + fence).
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        UP_BEGIN();
         bar_consumers();
+        UP_END(up_bar);
         if (TP && KIND == 3) {
             // tensor parallel: one bulk store per rank, issued by threads 0 .. tp-1, straight into slot tp_rank of that
             // rank's arena over NVLink (`out` is the byte offset of the slot) -- the sending half of the fused all-reduce
@@ -593,6 +719,15 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
     } else {
         flush_stores();
     }
+#ifdef QW_UNITPROF
+    UP_END(up_store);
+    if (p.prof && lane == 0) {
+        const int mi = (int) (&m - p.mat);
+        unsigned long long* up = p.prof + (size_t) gridDim.x * (p.L + 1) * kProfSlots + ((size_t) (blockIdx.x * 16 + warp) * 5 + mi) * 8;
+        up[0] += up_wait; up[1] += up_math; up[2] += up_epi; up[3] += up_units; up[4] += up_bar; up[5] += up_store;
+        up[6] += up_loop_end - up_entry - up_wait - up_math - up_epi;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------- consumer: prologues
@@ -1228,7 +1363,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
         for (int c = c0 + threadIdx.x; c < c1; c += kConsumerThreads) {
             const uint8_t* rec = row + (size_t) (c >> 8) * QW_SG_BYTES;
             const float sc = *reinterpret_cast<const float*>(rec + 256 + ((c >> 6) & 3) * 4);
-            stf_f32(p.flow_x0 + c, __fmul_rn((float) reinterpret_cast<const int8_t*>(rec)[c & 255], sc));
+            stf_f32(p.flow_x0 + c, p.x_inject ? p.x_inject[c] : __fmul_rn((float) reinterpret_cast<const int8_t*>(rec)[c & 255], sc));
         }
         flush_stores();
     } else {
@@ -1247,7 +1382,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int code = (int) (int8_t) (((i < 4 ? cw.x : cw.y) >> (8 * (i & 3))) & 0xffu);
-                xr[i] = __fmul_rn((float) code, sc);
+                xr[i] = p.x_inject ? p.x_inject[rec * 256 + lane * 8 + i] : __fmul_rn((float) code, sc);
             }
         }
     }
@@ -1256,7 +1391,7 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
     if (tp) xprev = nullptr;
     const int nph = 4 * p.layers_run;
 #pragma unroll 1
-    for (int ph = 0; ph <= nph; ++ph) {
+    for (int ph = 4 * p.l_begin; ph <= nph; ++ph) {
         const int l = ph >> 2, k = ph == nph ? 4 : (ph & 3);
         float* fl = flow_layer(p, k == 4 ? 0 : l);
         const int lp = k == 4 ? p.L : l; // profile row
@@ -1289,6 +1424,11 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
                 if (tp) nparts = xprev ? p.tp : 0;
             }
             prologue_quant<TP>(sh, p, src, n, nw, nparts);
+        }
+        if (p.dbg_codes && blockIdx.x == 0) { // debug: what this GEMV is fed (every CTA holds the same vector)
+            const int pieces = (int) (qw_row_bytes(p.mat[k].n) / 16);
+            uint4* dst = reinterpret_cast<uint4*>(p.dbg_codes + (size_t) (k == 4 ? 4 * p.L : 4 * l + k) * p.dbg_stride);
+            for (int i = threadIdx.x; i < pieces; i += kConsumerThreads) dst[i] = reinterpret_cast<const uint4*>(sh.xq)[i];
         }
         stamp(p, lp, 4 * (k & 3) + 2);
         consume_mat<TP>(sh, p, p.mat[k], l, rp, out, resid);
@@ -1415,6 +1555,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(fit, atoi(e)));
     if (const char* e = getenv("QWEN_MEGA_MODE")) st->dbg_mode = atoi(e);
     if (const char* e = getenv("QWEN_MEGA_L2AHEAD")) st->l2_ahead = std::max(0, atoi(e));
+    if (const char* e = getenv("QWEN_MEGA_INFLIGHT")) st->inflight = std::max(0, atoi(e));
     if (getenv("QWEN_MEGA_VERBOSE")) fprintf(stderr, "[mega] nslot %d mode %d smem %d\n", st->nslot, st->dbg_mode, fixed);
     if (st->nslot < 2) {
         qw_set_error("persistent decode kernel: not enough shared memory for a 2-slot ring (%d bytes free)", avail);
@@ -1575,6 +1716,10 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.S = c->S; p.kv_mul = c->Hl / c->KVHl;
     p.pos = pos; p.token = token; p.token_dev = token_dev;
     p.layers_run = (c->layers_run >= 0 && c->layers_run <= c->L) ? c->layers_run : c->L;
+    p.l_begin = (c->layer_begin > 0 && c->layer_begin <= p.layers_run) ? c->layer_begin : 0;
+    p.x_inject = c->x_inject_on ? c->x_inject : nullptr;
+    p.dbg_codes = c->dbg_codes;
+    p.dbg_stride = (int) c->dbg_codes_stride;
     int stage_env = 1; // QWEN_MEGA_STAGE=0: per-warp stores + fence instead of the staged bulk store
     if (const char* e = getenv("QWEN_MEGA_STAGE")) stage_env = atoi(e);
     const int grid = st->grid;
@@ -1608,6 +1753,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.err = c->err_flag;
     p.dbg_mode = st->dbg_mode;
     p.l2_ahead = st->l2_ahead;
+    p.inflight = st->inflight < st->nslot ? st->inflight : 0;
     p.perm = st->perm;
     p.prof = st->prof;
     p.nslot = st->nslot; p.off_xq = st->off_xq; p.off_scr = st->off_scr;
@@ -1645,7 +1791,8 @@ const float* qw_mega_debug_ptr(QwenCudaCtx* c, const char* what) {
 int qw_mega_profile_enable(QwenCudaCtx* c) {
     MegaState* st = state_of(c);
     if (!st || !st->grid) return -1;
-    const size_t n = (size_t) st->grid * (c->L + 1) * kProfSlots;
+    // + per-warp GEMV cycle counters [grid][16 warps][5 matrices][8: wait, math, epilogue, units, end barrier, bulk store, entry] (filled by -DQW_UNITPROF builds)
+    const size_t n = (size_t) st->grid * (c->L + 1) * kProfSlots + (size_t) st->grid * 16 * 5 * 8;
     if (!st->prof) QW_CUDA(cudaMalloc((void**) &st->prof, n * 8));
     QW_CUDA(cudaMemset(st->prof, 0, n * 8));
     QW_CUDA(cudaDeviceSynchronize());
@@ -1658,7 +1805,7 @@ int qw_mega_tlog(QwenCudaCtx*, int, unsigned long long*) {
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
     MegaState* st = state_of(c);
     if (!st || !st->prof) return -1;
-    size_t n = (size_t) st->grid * (c->L + 1) * kProfSlots;
+    size_t n = (size_t) st->grid * (c->L + 1) * kProfSlots + (size_t) st->grid * 16 * 5 * 8;
     if (n > max_elems) n = max_elems;
     QW_CUDA(cudaStreamSynchronize(c->stream));
     QW_CUDA(cudaMemcpy(host, st->prof, n * 8, cudaMemcpyDeviceToHost));

@@ -175,9 +175,11 @@ int qw_attention_device(QwenCudaCtx* c, int layer, int pos, const float* q_dev, 
 int qw_decode_ops(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     cudaStream_t st = c->stream;
     const int D = c->D, Pl = c->Pl, Kl = c->Kl, Hdl = c->Hdl;
-    k_embed<<<(D + 255) / 256, 256, 0, st>>>(c->x, c->w_emb, token, token_dev, D);
     const int layers = (c->layers_run >= 0 && c->layers_run <= c->L) ? c->layers_run : c->L;
-    for (int l = 0; l < layers; ++l) {
+    const int l0 = (c->layer_begin > 0 && c->layer_begin <= layers) ? c->layer_begin : 0; // debug window (qwen_cuda_debug_set_window)
+    if (c->x_inject_on) QW_CUDA(cudaMemcpyAsync(c->x, c->x_inject, (size_t) D * 4, cudaMemcpyDeviceToDevice, st));
+    else k_embed<<<(D + 255) / 256, 256, 0, st>>>(c->x, c->w_emb, token, token_dev, D);
+    for (int l = l0; l < layers; ++l) {
         const size_t loff = (size_t) l * c->KVHl * c->S * 128;
         launch_rmsnorm(c->xb, c->x, c->att_norm + (size_t) l * D, D, st);
         quantize_padded(c, c->xb, D);

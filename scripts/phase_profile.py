@@ -17,7 +17,7 @@ n = ql.lib.qwen_cuda_debug_profile_enable(gm.ctx)
 gm.forward_nocopy(7, ctx + 8)
 buf = np.zeros(n, np.uint64)
 G = ql.lib.qwen_cuda_debug_profile_read(gm.ctx, buf.ctypes.data_as(C.c_void_p), n)
-t = buf.reshape(G, sh.n_layers + 1, 16).astype(np.int64)
+t = buf[: G * (sh.n_layers + 1) * 16].reshape(G, sh.n_layers + 1, 16).astype(np.int64)
 # stamp slots per layer: 4k = phase k start, 4k+2 = after its prologue, 4k+3 = after its GEMV; 5 = after attention + combine
 names = [("poll x + norm + quant", 0, 2), ("QKV gemv", 2, 3), ("attn: poll q, norm, rope", 4, 1), ("attn: tiles", 1, 9), ("attn: merge + publish", 9, 13), ("combine", 13, 5), ("poll att_q", 5, 6), ("WO gemv", 6, 7),
          ("poll x + norm + quant", 8, 10), ("W13 gemv", 10, 11), ("poll h + quant", 12, 14), ("W2 gemv", 14, 15)]

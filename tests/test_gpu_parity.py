@@ -539,25 +539,34 @@ def test_persistent_kernel_is_deterministic(qlib, pkg, ckpt_dir):
 
 
 @pytest.mark.parametrize("shape_name", ["4b-l2", "tiny-untied"])
-def test_staged_bulk_store_publish_equals_per_warp_stores(qlib, pkg, ckpt_dir, shape_name, monkeypatch):
+def test_staged_bulk_store_publish_matches_per_warp_stores(qlib, pkg, ckpt_dir, shape_name, monkeypatch):
     """The persistent kernel publishes each CTA's GEMV rows with one TMA bulk store from shared memory (row ranges in
-    units of 4 rows); QWEN_MEGA_STAGE=0 selects the older per-warp stores + fence with rows split to the row. Only the
-    way results travel differs, so the logits must be bit-identical, including across a context that switches modes
-    between steps (the variable is read per launch)."""
+    units of 4 rows); QWEN_MEGA_STAGE=0 selects the older per-warp stores + fence with rows split to the row. Only the way
+    results travel differs -- and, since the row ranges differ, which row of a two-row work unit a given row is (the two
+    rows of a unit put their tail groups on different lanes, so the fp32 order of a row's group terms can differ in the
+    last bit). Logits must agree to fp32 rounding noise, each mode must be bit-reproducible, and a context may switch
+    modes between steps (the variable is read per launch)."""
     path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, shape_name, seed=11)
     V = pkg.checkpoint.SHAPES[shape_name].vocab_size
     toks = [int(t) for t in np.random.default_rng(8).integers(0, V, size=10)]
     outs = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("QWEN_MEGA_STAGE", mode)
+    for mode in ("1", "0", "1b", "0b"):
+        monkeypatch.setenv("QWEN_MEGA_STAGE", mode[0])
         with qlib.open(path, 32) as gm:
             outs[mode] = [gm.forward(t, pos) for pos, t in enumerate(toks)]
-    for x, y in zip(outs["1"], outs["0"]):
+    for x, y in zip(outs["1"], outs["1b"]):
         same(x, y)
-    with qlib.open(path, 32) as gm:  # alternate per step
+    for x, y in zip(outs["0"], outs["0b"]):
+        same(x, y)
+    for x, y in zip(outs["1"], outs["0"]):
+        assert np.abs(x - y).max() <= NOISE_CAP * max(1.0, float(x.std())), np.abs(x - y).max()
+    within = sum(not (np.abs(x - y) > ATOL + RTOL * np.abs(y)).any() for x, y in zip(outs["1"], outs["0"]))
+    assert within >= len(toks) - 2, within  # a re-quantisation flip may separate a step or two (DESIGN.md 5)
+    with qlib.open(path, 32) as gm:  # alternate per step: every step must stay close to the single-mode runs
         for pos, t in enumerate(toks):
             monkeypatch.setenv("QWEN_MEGA_STAGE", str(pos & 1))
-            same(gm.forward(t, pos), outs["1"][pos])
+            lg = gm.forward(t, pos)
+            assert np.abs(lg - outs["1"][pos]).max() <= NOISE_CAP * max(1.0, float(lg.std()))
 
 
 def test_4b_full_shape_first_tokens(qlib, oracle, pkg, ckpt_dir):

