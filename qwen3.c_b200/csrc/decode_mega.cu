@@ -138,9 +138,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) { // `count` arrivals at once
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -550,13 +547,10 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
 #pragma unroll 1
     for (int t0 = 0; t0 < total; t0 += upt, rp.next(p.nslot)) {
         const int t1 = min(t0 + upt, total);
-        // Only the warps that own a unit of the tile touch it (measured: walking a tile -- wait, __syncwarp, arrive -- cost a
-        // warp ~400 cycles, and with 5 units per tile two thirds of a warp's tile visits were for nothing: 28 % of the
-        // w1/w3 phase). The slot's `empty` barrier still counts 15 arrivals: the owner of the tile's first unit brings the
-        // arrivals of the warps that have no unit here.
-        if (u >= t1) continue;
+        // Every warp visits every tile, owner of a unit or not: a warp that skipped tiles could no longer tell the phases of
+        // a slot's mbarrier apart (parity waits alias once a waiter is more than one phase away) -- tried, it reads tiles
+        // that have not landed. The visit (wait, __syncwarp, arrive) costs ~400 cycles: 28 % of the w1/w3 phase.
         const unsigned slot = rp.slot, par = rp.par;
-        const uint32_t arrivals = u == t0 ? (uint32_t) (kConsumerWarps + 1 - min(t1 - t0, kConsumerWarps)) : 1u;
         UP_BEGIN();
         mbar_wait(sh, p, sh.full + slot * 8, par, 3);
         UP_END(up_wait);
@@ -624,7 +618,7 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
                 // this warp's last unit in the tile: every byte it needs from the ring slot has been consumed by a
                 // dp4a, so the slot goes back to the producer BEFORE the cross-lane reduction and the epilogue
                 __syncwarp();
-                if (lane == 0) mbar_arrive_n(sh.empty + slot * 8, arrivals);
+                if (lane == 0) mbar_arrive(sh.empty + slot * 8);
                 released = true;
             }
             // Cross-lane reduction and epilogue, for TWO units (4 rows) at a time: the first unit's lane partials wait in
@@ -676,9 +670,9 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
             ++up_units;
 #endif
         }
-        if (!released) { // debug mode 1 only (math skipped)
+        if (!released) { // no unit of this warp in the tile
             __syncwarp();
-            if (lane == 0) mbar_arrive_n(sh.empty + slot * 8, arrivals);
+            if (lane == 0) mbar_arrive(sh.empty + slot * 8);
         }
     }
 #ifdef QW_UNITPROF
