@@ -181,6 +181,10 @@ int qwen_cuda_matmul_group_dots(int32_t* dots, const int8_t* xq, const int8_t* w
  * reps >= 1 runs of the kernel, *ms (optional) = best device time of one run. */
 int qwen_cuda_matmul_batch(float* out, int32_t* dots, const int8_t* xq, const float* xs, const int8_t* wq,
                            const float* ws, int n, int d, int T, int reps, float* ms);
+/* Measured dense int8 tensor throughput of the device in tera-ops/s (2 ops per MAC): `iters` back-to-back
+ * tcgen05.mma.kind::i8 M128 N256 K32 per SM on resident operands, best of `reps` runs. bench.py's prefill fraction is
+ * quoted against this number, not the nominal 4.5 POPS. */
+int qwen_cuda_int8_peak(int iters, int reps, float* tops);
 int qwen_cuda_rmsnorm(float* out, const float* x, const float* w, int size);                /* forward.c:12-28 */
 int qwen_cuda_softmax(float* x, int size);                                                  /* forward.c:34-77 */
 /* cos/sin: head_dim/2 host-computed values for this position (forward.c:109-110). */

@@ -74,6 +74,7 @@ struct MatDesc {
     int rows, n, gran;   // rows, columns, granularity of the per-CTA row split
     int rt;              // rows per ring tile
     int stage;           // 1: results are collected in shared memory and leave as ONE bulk store per CTA (see consume_mat)
+    int C, cr;           // per-warp streaming variant: chunks per row and records per chunk (decode_pw.cuh)
     int kind;            // epilogue: 0 out[row] = v, 1 out[row] = resid[row] + v, 2 out[row/2] = silu(v0) * v1,
                          // 3 tensor parallel: this rank's partial v goes to slot tp_rank of EVERY rank's arena (peer stores)
 };
@@ -125,6 +126,7 @@ struct MegaState {
     int attn_ga = 0, part_stride = 0;
     float* peer[2][kMaxTp] = {};  // mapped arenas of every rank (cudaIpc), [parity][rank]; own entries = arena[parity]
     bool peers_open = false;
+    bool pw = false;              // per-warp streaming variant (decode_pw.cuh): single-GPU contexts
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -1431,6 +1433,8 @@ __device__ void consumer(const Shared& sh, const MegaParams& p) {
     }
 }
 
+#include "decode_pw.cuh"
+
 // one instantiation per GQA ratio: only the attention code of the model at hand is in the kernel
 template <int KV_MUL, bool TP>
 __global__ void __launch_bounds__(kThreads, 1) k_decode(const __grid_constant__ MegaParams p) {
@@ -1482,6 +1486,14 @@ __global__ void k_fill_u32(uint32_t* dst, size_t n, uint32_t v) {
 
 // ---------------------------------------------------------------- host side
 static MegaState* state_of(QwenCudaCtx* c) { return reinterpret_cast<MegaState*>(c->mega); }
+static const void* decode_kernel_pw(int kv_mul) {
+    switch (kv_mul) {
+        case 1: return (const void*) k_decode_pw<1>;
+        case 2: return (const void*) k_decode_pw<2>;
+        case 4: return (const void*) k_decode_pw<4>;
+        default: return (const void*) k_decode_pw<8>;
+    }
+}
 static const void* decode_kernel(int kv_mul, bool tp) {
     switch (kv_mul) {
         case 1: return tp ? (const void*) k_decode<1, true> : (const void*) k_decode<1, false>;
@@ -1535,7 +1547,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     // everything except the ring first, then give the ring all remaining slots
     const int xq_b = (int) qw_row_bytes(amax);
     const int scr_b = std::max(kScrFloats, (kv_mul + 2) * 128) * 4;
-    const int misc_b = 1024, bar_b = 2 * kMaxSlots * 8;
+    const int misc_b = 1024, bar_b = std::max(2 * kMaxSlots * 8, 3 * kConsumerWarps * 8);
     const int xres_b = c->tp_size > 1 ? qw_pad_cols(c->D) * 4 : 0; // tensor parallel: the residual stream lives in every CTA
     const int fixed = ((xq_b + 127) & ~127) + ((scr_b + 127) & ~127) + ((misc_b + 127) & ~127) + ((bar_b + 127) & ~127)
                       + ((xres_b + 127) & ~127);
@@ -1544,6 +1556,10 @@ int qw_mega_init(QwenCudaCtx* c) {
     // 1.826 / 1.886 ms per token with 7 / 6 / 5 / 4 slots, 8B shape 2.459 (7) vs 2.426 (5): fewer bulk copies in flight per
     // SM shorten every hand-off (scripts/ubench/handoff.cu: 13 us at 6 x 28 KB in flight, 3.3 us at 2) by more than the
     // shallower prefetch costs. QWEN_MEGA_NSLOT overrides (up to what fits).
+    // Single-GPU contexts run the per-warp streaming variant (decode_pw.cuh) when its 15 warp regions fit beside the
+    // activation vector; QWEN_MEGA_PW=0 selects the ring variant (the kernel of tensor-parallel contexts).
+    st->pw = c->tp_size == 1 && avail >= kConsumerWarps * kPwRegion && qw_sg_per_row(c->D) >= 1;
+    if (const char* e = getenv("QWEN_MEGA_PW")) st->pw = st->pw && atoi(e) != 0;
     const int fit = std::min(kMaxSlots, avail / kSlotBytes);
     st->nslot = std::min(fit, 5);
     if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(fit, atoi(e)));
@@ -1555,16 +1571,17 @@ int qw_mega_init(QwenCudaCtx* c) {
         qw_set_error("persistent decode kernel: not enough shared memory for a 2-slot ring (%d bytes free)", avail);
         return -1;
     }
-    take(st->nslot * kSlotBytes);
+    take(st->pw ? kConsumerWarps * kPwRegion : st->nslot * kSlotBytes);
     st->off_xq = take(xq_b);
     st->off_scr = take(scr_b);
     st->off_misc = take(misc_b);
     st->off_bar = take(bar_b);
     st->off_xres = take(xres_b);
     st->smem = off;
-    QW_CUDA(cudaFuncSetAttribute(decode_kernel(kv_mul, c->tp_size > 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
+    const void* kern = st->pw ? decode_kernel_pw(kv_mul) : decode_kernel(kv_mul, c->tp_size > 1);
+    QW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
     int per_sm = 0;
-    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel(kv_mul, c->tp_size > 1), kThreads, st->smem));
+    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, st->pw ? kConsumerThreads : kThreads, st->smem));
     if (per_sm < 1) {
         qw_set_error("persistent decode kernel does not fit on an SM (smem %zu)", st->smem);
         return -1;
@@ -1725,7 +1742,8 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         const int sg = kind == 2 ? 8 : 4;
         const bool stage = stage_env && rows % sg == 0 && (rows / sg / grid + 1) * sg <= kScrFloats;
         const int gran = stage ? sg : (kind == 2 ? 2 : 1);
-        return MatDesc{base, stride, rows, n, gran, rt, stage ? 1 : 0, kind};
+        const int recs = qw_sg_per_row(n), C = (recs + kPwChunkRecs - 1) / kPwChunkRecs, cr = (recs + C - 1) / C;
+        return MatDesc{base, stride, rows, n, gran, rt, stage ? 1 : 0, C, cr, kind};
     };
     p.mat[0] = desc(c->w_qkv, c->w_qkv_stride, c->Pl + 2 * c->Kl, c->D, 0);
     const int kres = c->tp_size > 1 ? 3 : 1; // wo / w2 epilogue: residual add on one GPU, partial push under tensor parallelism
@@ -1754,7 +1772,10 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.off_misc = st->off_misc; p.off_bar = st->off_bar;
     void* args[] = {&p};
     // cooperative launch: the CTAs wait for each other's results, so all of them must be resident
-    QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul, c->tp_size > 1), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
+    if (st->pw)
+        QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel_pw(p.kv_mul), dim3(st->grid), dim3(kConsumerThreads), args, st->smem, c->stream));
+    else
+        QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul, c->tp_size > 1), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
     st->last_layers = p.layers_run;
     ++st->launches;
     // the classifier is split over vocabulary rows: gather the logits slices

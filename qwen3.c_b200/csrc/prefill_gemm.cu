@@ -295,6 +295,42 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
 }
 
+// Measured int8 tensor peak (MEASURED_PEAKS.json has no int8 figure, "the builder must measure it on the
+// box"): every CTA issues `iters` back-to-back tcgen05.mma.cta_group::1.kind::i8 M128 N256 K32 on resident shared-memory
+// operands into one TMEM accumulator -- no loads, no promotion, no epilogue. The operand bytes are whatever shared memory
+// holds; integer MMAs have no data-dependent timing.
+__global__ void __launch_bounds__(128, 1) k_int8_peak(int iters, int* err) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (128 + 256) * 64 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u * (uint32_t) (i & 3);
+    if (threadIdx.x == 0) {
+        mb_init(s_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp == 0 && lane == 0) {
+        const uint32_t idesc = umma_idesc_i8(128, 256);
+        const uint32_t a = s_u32(smem), b = s_u32(smem) + 128 * 64;
+        for (int i = 0; i < iters; ++i) umma_i8(tmem_base, umma_desc_sw64(a + 32 * (i & 1)), umma_desc_sw64(b + 32 * (i & 1)), idesc, 1);
+        umma_commit(s_u32(&bar));
+        mb_wait(s_u32(&bar), 0, err, 9);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -456,4 +492,44 @@ extern "C" int qwen_cuda_matmul_batch(float* out, int32_t* dots, const int8_t* x
     free(xsT);
     cudaFree(dwq); cudaFree(dws); cudaFree(dw); cudaFree(dxq); cudaFree(dxsT); cudaFree(dout); cudaFree(derr); cudaFree(ddots);
     return rc;
+}
+
+// Measured dense int8 tensor throughput of this device (tera-ops/s, 2 ops per MAC): see k_int8_peak. Best of `reps` runs.
+extern "C" int qwen_cuda_int8_peak(int iters, int reps, float* tops) {
+    if (qwen_cuda_device_count() <= 0) {
+        qw_set_error("no CUDA device: this library has no CPU path");
+        return -1;
+    }
+    if (iters < 1 || reps < 1 || !tops) return -2;
+    int dev = 0, sms = 0;
+    QW_CUDA(cudaGetDevice(&dev));
+    QW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int* derr = nullptr;
+    QW_CUDA(cudaMalloc(&derr, 4));
+    QW_CUDA(cudaMemset(derr, 0, 4));
+    const size_t smem = (128 + 256) * 64 + 1024;
+    cudaEvent_t e0, e1;
+    QW_CUDA(cudaEventCreate(&e0));
+    QW_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r <= reps; ++r) { // run 0 warms up
+        QW_CUDA(cudaEventRecord(e0, 0));
+        k_int8_peak<<<sms, 128, smem, 0>>>(iters, derr);
+        QW_CUDA(cudaEventRecord(e1, 0));
+        QW_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        QW_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0 && ms < best) best = ms;
+    }
+    int herr = 0;
+    QW_CUDA(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
+    cudaFree(derr);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (herr) {
+        qw_set_error("int8 peak: the MMA chain did not retire (wait %d timed out)", herr);
+        return -1;
+    }
+    *tops = (float) (2.0 * 128 * 256 * 32 * (double) iters * sms / (best * 1e-3) / 1e12);
+    return 0;
 }
