@@ -35,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
+KERNEL_TAG = "k_decode_pw"  # the decode kernel single-GPU contexts run (csrc/decode_pw.cuh); ncu captures are tagged with it
 CKPT_DIR = os.environ.get("QWEN3_B200_CKPT_DIR", "/tmp/qwen3_b200_ckpt")
 WORKLOADS = {
     "4b-decode-ctx4096": ("4b", 4096),
@@ -176,6 +177,35 @@ def cpu_reference_run(path, seq_len, pos0, steps, warmup, budget_s=150.0):
                       f"{ob.cpu_model()}, OMP_WAIT_POLICY={os.environ.get('OMP_WAIT_POLICY')}"}
 
 
+def measured_int8_peak(ql):
+    """Dense int8 tensor throughput measured on this device (tcgen05.mma.kind::i8 M128 N256 K32 back to back on resident
+    operands, csrc/prefill_gemm.cu:k_int8_peak), tera-ops/s; the nominal 4.5 POPS only if the measurement fails."""
+    try:
+        ql.lib.qwen_cuda_int8_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
+        t = C.c_float(0)
+        if ql.lib.qwen_cuda_int8_peak(20000, 3, C.byref(t)) == 0 and t.value > 0:
+            return float(t.value), "measured in this run (qwen_cuda_int8_peak: tcgen05.mma.kind::i8 M128 N256 K32, no loads, no epilogue)"
+    except Exception:
+        pass
+    return 4500.0, "nominal dense int8 (measurement failed)"
+
+
+def single_gpu_decode(pkg, ql, shape_name, ctx, K, W):
+    """Device-timed decode of `shape_name` on ONE GPU (this process's current device): the same-workload base of the
+    tensor-parallel lines (the scaling curve must divide like by like)."""
+    path = ensure_ckpt(pkg, shape_name)
+    t = time.time()
+    gm = ql.open(path, ctx + W + K + 8)
+    create_s = time.time() - t
+    ms, _ = gm.time_decode(7, ctx, K, W)
+    gm.close()
+    shape = pkg.checkpoint.SHAPES[shape_name]
+    bytes_tok = float(np.mean([shape.decode_bytes(ctx + W + i) for i in range(K)]))
+    peak, _ = measured_peak()
+    return {"workload": f"{shape_name}-decode-ctx{ctx}", "n_gpus": 1, "value": K / (ms / 1e3), "unit": "tok/s", "ms_per_step": ms / K,
+            "hbm_frac": bytes_tok * K / (ms / 1e3) / 1e9 / peak, "model_create_s": create_s}
+
+
 def _timed(fn):
     t0 = time.perf_counter()
     if not fn():
@@ -191,6 +221,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tp-base", action="store_true", help="skip the 8B one-GPU figure on the N=1 line")
     ap.add_argument("--path", default="mega", choices=["mega", "ops"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -233,7 +264,8 @@ def main():
     path = ensure_ckpt(pkg, shape_name)
     t = time.time()
     gm = ql.open(path, seq_len)
-    log(f"[bench] model_create {time.time() - t:.1f}s")
+    model_create_s = time.time() - t
+    log(f"[bench] model_create {model_create_s:.1f}s")
     gm.set_path(0 if args.path == "mega" else 1)
 
     sampler = ClockSampler(0)
@@ -293,15 +325,19 @@ def main():
                 e2e={"value": K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": shape.vocab_size * 4},
                 roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                           "traffic": None, "peak_source": peak_src, "bytes_per_token": bytes_tok,
-                          "kernel": "k_decode (persistent, 1 launch/token)" if args.path == "mega" else "per-op kernels",
+                          "kernel": KERNEL_TAG + " (persistent, 1 launch/token)" if args.path == "mega" else "per-op kernels",
                           "frac_of_8TBs_nominal": achieved / 8000.0})
     line["config"]["path"] = args.path
+    line["model_create_s"] = model_create_s
     line["sampled_generation"] = sampled
-    try:  # dram bytes per launch of k_decode from the committed ncu capture of this workload (profiles/r1_traffic.json)
-        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
-        if args.path == "mega" and workload in tr:
-            line["roofline"]["traffic"] = tr[workload]["traffic"]
-            line["roofline"]["traffic_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_traffic.json)"
+    try:  # dram bytes per launch from this round's ncu capture -- only if it was taken on the kernel variant that just ran
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        ent = tr.get(workload)
+        overridden = [k for k in os.environ if k.startswith("QWEN_MEGA_")]
+        if args.path == "mega" and ent and ent.get("kernel") == KERNEL_TAG and not overridden:
+            line["roofline"]["traffic"] = ent["traffic"]
+            line["roofline"]["traffic_source"] = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of %s, captured at commit %s "
+                                                  "(profiles/r2_traffic.json); not re-measured in this run" % (ent["kernel"], ent.get("commit", "?")))
     except Exception:
         pass
     # (3) prompt prefill on the same model (north_star: prefill tok/s + int8 tensor-pipe fraction): 512 tokens at
@@ -312,14 +348,21 @@ def main():
         gm.prefill_nocopy(toks, 0)
         best = min(_timed(lambda: gm.prefill_nocopy(toks, 0)) for _ in range(3))
         macs = Tp * (shape.weight_elements() - shape.vocab_size * shape.dim)  # layer GEMMs; the classifier runs for the last token only
+        peak_i8, peak_i8_src = measured_int8_peak(ql)
         line["prefill"] = {"workload": f"{shape_name}-prefill{Tp}", "tok_s": Tp / best, "ms": 1e3 * best,
-                           "int8_tops": 2 * macs / best / 1e12, "peak_tops": 4500.0,
-                           "frac": 2 * macs / best / 1e12 / 4500.0,
-                           "peak_source": "nominal dense int8 (4.5 POPS); MEASURED_PEAKS.json has no int8 figure",
+                           "int8_tops": 2 * macs / best / 1e12, "peak_tops": peak_i8,
+                           "frac": 2 * macs / best / 1e12 / peak_i8,
+                           "peak_source": peak_i8_src,
                            "note": "group-scaled GEMM: the fp32 promotion of every 64-wide group runs on the CUDA cores"}
     except Exception as e:  # never lose the decode number
         line["prefill"] = {"error": repr(e)}
     gm.close()
+    if workload == "4b-decode-ctx4096" and not args.no_tp_base:
+        # the tensor-parallel lines (N >= 2) run the 8B shape: its one-GPU figure, so that the 1 -> 8 curve divides like by like
+        try:
+            line["tp_base"] = single_gpu_decode(pkg, ql, "8b", 4096, K, W)
+        except Exception as e:
+            line["tp_base"] = {"error": repr(e)}
     if not args.no_cpu_baseline:
         try:
             r = cpu_reference_run(path, seq_len, pos0, 6, 1, budget_s=25.0)

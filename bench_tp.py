@@ -15,7 +15,7 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
     import torch
     import torch.distributed as dist
 
-    from bench import ClockSampler, ensure_ckpt, log, measured_peak
+    from bench import ClockSampler, cpu_reference_run, ensure_ckpt, log, measured_peak, single_gpu_decode
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -32,8 +32,9 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
     t = time.time()
     gm = ql.open(path, seq_len)
     pkg.tp.init_tensor_parallel(ql, gm, rank, world, dist)
+    model_create_s = time.time() - t
     if rank == 0:
-        log(f"[bench] tp={world} model_create + nccl init {time.time() - t:.1f}s")
+        log(f"[bench] tp={world} model_create + nccl init {model_create_s:.1f}s")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -46,6 +47,7 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
 
     dist.barrier()
     torch.cuda.synchronize()
+    fused = gm.get_path() == 0
     ms, launches = gm.time_decode(7, ctx, K, W)
     torch.cuda.synchronize()
     dist.barrier()
@@ -59,12 +61,21 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
             raise SystemExit("forward failed: " + ql.err())
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
+    gm.close()
+    dist.barrier()
+    if rank == 0:
+        # the same workload on ONE GPU, measured now on rank 0's device: the base of the scaling curve
+        os.environ.pop("QWEN_CUDA_TP_RANK", None)
+        os.environ.pop("QWEN_CUDA_TP_SIZE", None)
+        try:
+            tp1 = single_gpu_decode(pkg, ql, shape_name, ctx, K, W)
+        except Exception as e:
+            tp1 = {"error": repr(e)}
     if rank == 0:
         tok_s = K / (ms / 1e3)
         bytes_tok = float(np.mean([shape.decode_bytes(ctx + W + i) for i in range(K)]))
         peak, peak_src = measured_peak()
         achieved = bytes_tok / world * tok_s / 1e9  # per-GPU share of the algorithmic bytes
-        fused = gm.get_path() == 0
         line = dict(base, value=tok_s, ms_per_step=ms / K, dtype="int8xint8->int32, fp32", clocks=clocks,
                     gpu_launches=launches if fused else launches + K * (2 * shape.n_layers + 1),
                     e2e={"value": K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": shape.vocab_size * 4},
@@ -75,8 +86,18 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
                               else "per-op kernels + NCCL all-reduce (peer mapping unavailable)"})
         line["config"]["parallelism"] = f"tp{world}"
         line["config"]["path"] = "mega+peer-stores" if fused else "ops+nccl"
+        line["model_create_s"] = model_create_s
+        line["tp1_same_workload"] = tp1
+        if "value" in tp1:
+            line["vs_tp1_same_workload"] = tok_s / tp1["value"]
+        if not args.no_cpu_baseline:
+            try:
+                r = cpu_reference_run(path, seq_len, ctx, 4, 1, budget_s=40.0)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "tok/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                        "all_cores": r["all_cores"], "sweep": r["sweep"]}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         print(json.dumps(line), flush=True)
-    gm.close()
     dist.barrier()
     dist.destroy_process_group()
     return 0

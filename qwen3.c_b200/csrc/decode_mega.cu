@@ -88,6 +88,9 @@ struct MegaParams {
     int dbg_stride;
     int perm;       // CTA -> row-block permutation multiplier (coprime to the grid)
     int dbg_mode;   // 0 normal; 1 consumers skip the GEMV math (ring throughput test)
+    int pw_late;    // per-warp variant: 1 = a phase's first weight items are issued after its hand-off polls, not before
+    int pw_pub;     // per-warp variant: 0 = results leave as one TMA bulk store per CTA, 1 = plain stores by warp 0 + fence
+    int l2_cls;     // bytes of this CTA's classifier rows to prefetch into L2 ahead of the classifier phase
     int inflight;   // producer: at most this many bulk-copy tiles in flight per SM (0 = the ring depth)
     int l2_ahead;   // 0: no L2 prefetch; else prefetch the next sub-phase (and this many 32 KB pieces of the classifier)
     const int* token_dev;
@@ -386,7 +389,7 @@ __device__ __noinline__ void prefetch_subphase(const MegaParams& p, int sp) {
         cta_rows(m, p.perm, r0, r1);
         const size_t rb = qw_row_bytes(m.n);
         size_t bytes = (size_t) (r1 - r0) * rb;
-        if (k == 5) bytes = min(bytes, (size_t) p.l2_ahead * 32768); // the classifier is far larger than L2's share
+        if (k == 5) bytes = min(bytes, (size_t) p.l2_cls); // the classifier is far larger than L2's share
         prefetch_l2(m.base + (k == 5 ? 0 : (size_t) l * m.stride) + (size_t) r0 * rb, bytes);
     }
 }
@@ -1564,6 +1567,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     st->nslot = std::min(fit, 5);
     if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(fit, atoi(e)));
     if (const char* e = getenv("QWEN_MEGA_MODE")) st->dbg_mode = atoi(e);
+    if (st->pw) st->l2_ahead = 2; // per-warp variant: HBM -> L2 prefetch two sub-phases ahead (decode_pw.cuh: pw_prefetcher)
     if (const char* e = getenv("QWEN_MEGA_L2AHEAD")) st->l2_ahead = std::max(0, atoi(e));
     if (const char* e = getenv("QWEN_MEGA_INFLIGHT")) st->inflight = std::max(0, atoi(e));
     if (getenv("QWEN_MEGA_VERBOSE")) fprintf(stderr, "[mega] nslot %d mode %d smem %d\n", st->nslot, st->dbg_mode, fixed);
@@ -1581,7 +1585,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     const void* kern = st->pw ? decode_kernel_pw(kv_mul) : decode_kernel(kv_mul, c->tp_size > 1);
     QW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st->smem));
     int per_sm = 0;
-    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, st->pw ? kConsumerThreads : kThreads, st->smem));
+    QW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, st->smem));
     if (per_sm < 1) {
         qw_set_error("persistent decode kernel does not fit on an SM (smem %zu)", st->smem);
         return -1;
@@ -1740,7 +1744,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         if (rt < 2 && kind == 2) rt = 2;
         // staged bulk store: a CTA's slice of the output must start and end on 16 bytes (4 rows; 8 for the w1/w3 pairs)
         const int sg = kind == 2 ? 8 : 4;
-        const bool stage = stage_env && rows % sg == 0 && (rows / sg / grid + 1) * sg <= kScrFloats;
+        const bool stage = stage_env && rows % sg == 0 && (rows / sg / grid + 1) * sg <= (kind == 2 ? 2048 : kScrFloats); // kind 2: raw sums wait at +2048 (decode_pw.cuh)
         const int gran = stage ? sg : (kind == 2 ? 2 : 1);
         const int recs = qw_sg_per_row(n), C = (recs + kPwChunkRecs - 1) / kPwChunkRecs, cr = (recs + C - 1) / C;
         return MatDesc{base, stride, rows, n, gran, rt, stage ? 1 : 0, C, cr, kind};
@@ -1765,6 +1769,10 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.err = c->err_flag;
     p.dbg_mode = st->dbg_mode;
     p.l2_ahead = st->l2_ahead;
+    if (const char* e = getenv("QWEN_PW_LATE")) p.pw_late = atoi(e);
+    if (const char* e = getenv("QWEN_PW_PUB")) p.pw_pub = atoi(e);
+    p.l2_cls = st->pw ? 384 * 1024 : st->l2_ahead * 32768;
+    if (const char* e = getenv("QWEN_MEGA_L2CLS_KB")) p.l2_cls = std::max(0, atoi(e)) * 1024;
     p.inflight = st->inflight < st->nslot ? st->inflight : 0;
     p.perm = st->perm;
     p.prof = st->prof;
@@ -1773,7 +1781,7 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     void* args[] = {&p};
     // cooperative launch: the CTAs wait for each other's results, so all of them must be resident
     if (st->pw)
-        QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel_pw(p.kv_mul), dim3(st->grid), dim3(kConsumerThreads), args, st->smem, c->stream));
+        QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel_pw(p.kv_mul), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
     else
         QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul, c->tp_size > 1), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
     st->last_layers = p.layers_run;

@@ -26,6 +26,6 @@ for mi, nm in enumerate(("QKV", "WO", "W13", "W2", "CLS")):
     div = L if mi < 4 else 1
     w, m, ep, units, bar, store, other = (up[:, :, mi, k] / div for k in range(7))
     tot = w + m + ep
-    print(f"  {nm:4s} units/warp {units.mean():5.2f} (max {units.max():.0f})  wait {w.mean():7.0f}  math {m.mean():7.0f}  epilogue {ep.mean():6.0f}  total {tot.mean():7.0f} (slowest warp {tot.max(axis=1).mean():7.0f})"
+    print(f"  {nm:4s} units/warp {units.mean():5.2f} (max {units.max():.0f})  load {w.mean():7.0f}  math {m.mean():7.0f}  epilogue {ep.mean():6.0f}  total {tot.mean():7.0f} (slowest warp {tot.max(axis=1).mean():7.0f})"
           f"  math/unit {m.sum() / max(units.sum(), 1):6.0f}  epi/unit {ep.sum() / max(units.sum(), 1):5.0f}"
-          f"  | end barrier {bar.mean():6.0f}  store (thread 0) {store[:, 0].mean():6.0f}  loop overhead {other.mean():6.0f}")
+          f"  | end barrier {bar.mean():6.0f}  store (thread 0) {store[:, 0].mean():6.0f}  loop overhead / issue {other.mean():6.0f}")

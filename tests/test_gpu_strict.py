@@ -244,3 +244,33 @@ def test_config1_06b_reference_cli_greedy_128(qlib, oracle, pkg, ckpt_dir):
                     pytest.xfail(f"streams differ at a genuine tie of the oracle (pos {pos}, margin {margin:.2e})")
                 tok = nxt
         raise AssertionError("CLI outputs differ but the token replay found no differing step")
+
+
+# ---------------------------------------------------------------- prefill + device sampler inside the reference's loops
+def test_patched_reference_loops_print_the_same_text(qlib, oracle, pkg, ckpt_dir):
+    """oracle/_ref/qwen_b200_fast = the reference's CLI with integration/completion_fast.patch applied to a temporary copy of
+    src/completion.c (prompt -> forward_prefill, generation -> qwen_cuda_forward_async + qwen_cuda_sample with host
+    fallback, one RNG draw per prompt token in chat mode), every other file the reference's own, linked against
+    libqwen3.so. It must print what the reference's CPU build prints: completion mode greedy and sampled, and a chat turn
+    (stdin: one message, then an empty line)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fast, ref = (os.path.join(here, "oracle", "_ref", n) for n in ("qwen_b200_fast", "qwen_ref"))
+    if not (os.path.exists(fast) and os.path.exists(ref)):
+        pytest.skip("oracle/_ref/qwen_b200_fast / qwen_ref not built (they need the reference tree at build time)")
+    shape = "tiny-untied"
+    path = pkg.checkpoint.ensure_checkpoint(ckpt_dir, shape, seed=11)
+    sh = pkg.checkpoint.SHAPES[shape]
+    if not os.path.exists(path + ".tokenizer"):
+        pkg.checkpoint.write_tokenizer(path + ".tokenizer", sh.vocab_size)
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    runs = [(["-m", "completion", "-i", "Qwen on B200", "-c", "64", "-t", "0", "-p", "0.9", "-s", "1"], None),
+            (["-m", "completion", "-i", "abcdefgh", "-c", "40", "-t", "1", "-p", "0.9", "-s", "33"], None),
+            (["-m", "chat", "-c", str(sh.seq_len), "-t", "0", "-p", "0.9", "-s", "7"], b"hello there\n\n")]
+    for args, stdin in runs:
+        outs = []
+        for exe in (ref, fast):
+            r = subprocess.run([exe, path] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=env)
+            assert r.returncode == 0, (exe, args, r.stderr[-800:])
+            outs.append(r.stdout)
+        assert len(outs[0]) > 40, ("the reference printed (almost) nothing", args)
+        assert outs[0] == outs[1], (args, outs[0][:300], outs[1][:300])
