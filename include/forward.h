@@ -5,7 +5,8 @@
  * so that src/completion.c:59,321 and src/sampler.c:196 link unchanged.
  *
  * forward() runs the whole token step on the device (one persistent sm_100a
- * kernel, csrc/decode.cu) and copies vocab_size logits into the pinned host
+ * kernel: csrc/decode_pw.cuh on one GPU, csrc/decode_mega.cu under tensor
+ * parallelism) and copies vocab_size logits into the pinned host
  * buffer it returns. The nine small ops and attention() are host-in / host-out
  * wrappers over single-op kernels (csrc/ops.cu); they exist for callers such as
  * the sampler's softmax() and for op-level parity tests, not for speed.

@@ -137,6 +137,10 @@ int qwen_cuda_set_path(QwenCudaCtx* ctx, int path);
  * all-reduce itself with NVLink peer stores), 1 if they fell back to per-op kernels + NCCL. */
 int qwen_cuda_get_path(const QwenCudaCtx* ctx);
 
+/* Bytes this context (= this tensor-parallel rank) holds in HBM -- weights in the kernels' layout, KV cache -- and the
+ * checkpoint bytes it read at create (a rank reads only the rows / column windows it owns). Any pointer may be NULL. */
+int qwen_cuda_memory(const QwenCudaCtx* ctx, size_t* weight_bytes, size_t* kv_bytes, size_t* read_bytes);
+
 /* ---- KV cache access (test + long-context parity hooks) ----------------------
  * Host side uses the reference's order: [npos][n_kv_heads*head_dim] for one layer
  * (reference: src/model.c:353-361, src/forward.c:244-248). */
@@ -159,11 +163,8 @@ int qwen_cuda_debug_set_window(QwenCudaCtx* ctx, int l0, int l1, const float* x_
  * classifier's input. read unpacks n codes and n / 64 scales of the last step (n = the GEMV's column count). */
 int qwen_cuda_debug_codes_enable(QwenCudaCtx* ctx, int on);
 int qwen_cuda_debug_codes_read(QwenCudaCtx* ctx, int which, int8_t* q, float* s, int n);
-/* Debug: per-CTA phase timestamps (globaltimer ns) of the persistent kernel, [grid][L+1][16].
- * enable returns the element count; read returns the grid size. */
-/* Debug: per-tile stamps of CTA 0 ([4][8192]: producer issue, consumer wait begin/end, done) for one
- * consumer warp; host == NULL arms the log, non-NULL reads it back. */
-int qwen_cuda_debug_tile_log(QwenCudaCtx* ctx, int warp, unsigned long long* host);
+/* Debug: per-CTA phase timestamps (globaltimer ns) of the persistent kernel, [grid][L+1][16] (+ per-warp cycle counters in
+ * -DQW_UNITPROF builds). enable returns the element count; read returns the grid size. */
 int qwen_cuda_debug_profile_enable(QwenCudaCtx* ctx);
 int qwen_cuda_debug_profile_read(QwenCudaCtx* ctx, unsigned long long* host, size_t max_elems);
 

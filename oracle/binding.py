@@ -85,6 +85,8 @@ class Oracle:
         L.orc_model_close.argtypes = [C.POINTER(_OrcModel)]
         L.orc_forward.restype = c_float_p
         L.orc_forward.argtypes = [C.POINTER(_OrcModel), C.c_int, C.c_int]
+        L.orc_forward_ex.restype = c_float_p
+        L.orc_forward_ex.argtypes = [C.POINTER(_OrcModel), C.c_int, C.c_int, C.c_int]
         L.orc_trace_enable.argtypes = [C.POINTER(_OrcModel)]
         L.orc_argmax.restype = C.c_int
         L.orc_argmax.argtypes = [c_float_p, C.c_int, c_float_p]
@@ -193,6 +195,10 @@ class OracleModel:
     def forward(self, token: int, pos: int) -> np.ndarray:
         ptr = self.orc.lib.orc_forward(self.h, token, pos)
         return np.ctypeslib.as_array(ptr, shape=(self.p.vocab_size,)).copy()
+
+    def forward_no_logits(self, token: int, pos: int) -> None:
+        """A prompt position: KV rows and residual stream as forward(), without the classifier matmul."""
+        self.orc.lib.orc_forward_ex(self.h, token, pos, 0)
 
     def _arr(self, ptr, n, dtype=np.float32):
         return np.ctypeslib.as_array(ptr, shape=(n,)).copy().astype(dtype, copy=False)

@@ -363,6 +363,12 @@ int orc_trace_enable(OrcModel* m) {
 
 /* reference: src/forward.c:225-350, step for step. */
 float* orc_forward(OrcModel* m, int token, int pos) {
+    return orc_forward_ex(m, token, pos, 1);
+}
+
+/* want_logits == 0: everything but the classifier matmul (:348) -- for prompt positions, whose logits the reference's
+ * loops compute and discard (src/completion.c:59-63); the KV cache and the residual stream are the same either way. */
+float* orc_forward_ex(OrcModel* m, int token, int pos, int want_logits) {
     const int D = m->dim, Hd = m->hidden_dim, hd = m->head_dim, gs = m->group_size;
     const int P = m->n_heads * hd, K = m->n_kv_heads * hd;
 
@@ -460,7 +466,9 @@ float* orc_forward(OrcModel* m, int token, int pos) {
         memcpy(m->tr_cls_in_q, m->aq, (size_t) D);
         memcpy(m->tr_cls_in_s, m->as, sizeof(float) * (size_t) (D / gs));
     }
-    orc_matmul(m->logits, m->aq, m->as, m->cls.q, m->cls.s, D, m->vocab_size, gs); /* :348 */
+    if (want_logits) {
+        orc_matmul(m->logits, m->aq, m->as, m->cls.q, m->cls.s, D, m->vocab_size, gs); /* :348 */
+    }
     return m->logits;
 }
 

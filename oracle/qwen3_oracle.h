@@ -97,6 +97,7 @@ OrcModel* orc_model_open(const char* path, int seq_len_override);
 void orc_model_close(OrcModel* m);
 int orc_trace_enable(OrcModel* m);
 float* orc_forward(OrcModel* m, int token, int pos);
+float* orc_forward_ex(OrcModel* m, int token, int pos, int want_logits);
 
 /* argmax with lowest-index tie break; margin = top1 - top2 (H7 bookkeeping). */
 int orc_argmax(const float* v, int n, float* margin);

@@ -168,7 +168,7 @@ struct QwenCudaCtx {
     size_t dbg_codes_stride;
     float* logits_pinned; // optional pinned bounce buffer
     float* sample_ws;     // workspace of the device sampler (sampler.cu), allocated on first use
-    size_t bytes_weights, bytes_kv;
+    size_t bytes_weights, bytes_kv, bytes_read; // HBM bytes of this rank's weights / KV cache; checkpoint bytes it read at create
 };
 
 // ops.cu -- launchers used by both the op-level ABI and the per-op decode path

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -30,43 +31,87 @@ int upload_f32(float** dst, const float* src, size_t n) {
     return 0;
 }
 
-// Staging area for one checkpoint tensor (plain layout) on its way to the SG layout.
-struct Stage {
-    int8_t* q = nullptr;
-    float* s = nullptr;
-    size_t cap = 0; // in codes
-    ~Stage() {
-        if (q) cudaFree(q);
-        if (s) cudaFree(s);
+// Upload pipeline (the reference maps the file and dequantises the whole embedding table on the host,
+// src/model.c:19-48, 199-206). A tensor slice travels in chunks of <= 32 MB of codes:
+//   host threads GATHER it from the page-cache mapping into one of three pinned staging buffers -- only the rows and the
+//   column window this rank owns, so a tensor-parallel rank reads 1/tp of every matrix instead of all of it --,
+//   cudaMemcpyAsync (pinned source: truly asynchronous, unlike the pageable mapping) into a device staging buffer,
+//   k_repack into the SG layout, all on the context's stream; an event per buffer says when it may be refilled.
+// The gather of chunk i+1 overlaps the copy and repack of chunk i.
+struct Uploader {
+    static constexpr int kBufs = 3;
+    static constexpr size_t kCodes = (size_t) 32 << 20;          // codes per chunk
+    uint8_t* pin[kBufs] = {};
+    int8_t* dq[kBufs] = {};
+    float* ds[kBufs] = {};
+    cudaEvent_t done[kBufs] = {};
+    bool used[kBufs] = {};
+    int next = 0, nthreads = 1;
+    size_t bytes_read = 0;
+    ~Uploader() {
+        for (int i = 0; i < kBufs; ++i) {
+            if (pin[i]) cudaFreeHost(pin[i]);
+            if (dq[i]) cudaFree(dq[i]);
+            if (ds[i]) cudaFree(ds[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
     }
-    int reserve(size_t codes) {
-        if (codes <= cap) return 0;
-        if (q) cudaFree(q);
-        if (s) cudaFree(s);
-        q = nullptr;
-        s = nullptr;
-        QW_CUDA(cudaMalloc((void**) &q, codes));
-        QW_CUDA(cudaMalloc((void**) &s, codes / 64 * 4 + 16));
-        cap = codes;
+    int init() {
+        for (int i = 0; i < kBufs; ++i) {
+            QW_CUDA(cudaHostAlloc((void**) &pin[i], kCodes + kCodes / 16, cudaHostAllocDefault));
+            QW_CUDA(cudaMalloc((void**) &dq[i], kCodes));
+            QW_CUDA(cudaMalloc((void**) &ds[i], kCodes / 16));
+            QW_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        nthreads = (int) std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("QWEN_CUDA_UPLOAD_THREADS")) nthreads = std::max(1, atoi(e));
+        return 0;
+    }
+    // rows [row0, row0 + rows) x columns [col0, col0 + n) of a [*][src_n] tensor -> dst rows dst_row0 + r * dst_row_step
+    int put(const QwenCudaQ8& t, int src_n, int row0, int rows, int col0, int n, uint8_t* dst, int dst_row0, int dst_row_step,
+            cudaStream_t stream) {
+        const int rows_per_chunk = (int) std::max<size_t>(1, kCodes / (size_t) n);
+        for (int r = 0; r < rows; r += rows_per_chunk) {
+            const int nr = std::min(rows_per_chunk, rows - r);
+            const int b = next;
+            next = (next + 1) % kBufs;
+            if (used[b]) QW_CUDA(cudaEventSynchronize(done[b]));
+            int8_t* hq = reinterpret_cast<int8_t*>(pin[b]);
+            float* hs = reinterpret_cast<float*>(pin[b] + kCodes);
+            const int8_t* sq = t.q + (size_t) (row0 + r) * src_n + col0;
+            const float* ss = t.s + ((size_t) (row0 + r) * src_n + col0) / 64;
+            auto gather = [=](int a, int e) {
+                if (n == src_n) { // whole rows: one contiguous range
+                    memcpy(hq + (size_t) a * n, sq + (size_t) a * src_n, (size_t) (e - a) * n);
+                    memcpy(hs + (size_t) a * (n / 64), ss + (size_t) a * (src_n / 64), (size_t) (e - a) * (n / 64) * 4);
+                } else {
+                    for (int i = a; i < e; ++i) {
+                        memcpy(hq + (size_t) i * n, sq + (size_t) i * src_n, (size_t) n);
+                        memcpy(hs + (size_t) i * (n / 64), ss + (size_t) i * (src_n / 64), (size_t) (n / 64) * 4);
+                    }
+                }
+            };
+            const int T = (size_t) nr * n < ((size_t) 1 << 20) ? 1 : std::min(nthreads, nr);
+            if (T <= 1) {
+                gather(0, nr);
+            } else {
+                std::vector<std::thread> th;
+                for (int k = 1; k < T; ++k) th.emplace_back(gather, (int) ((long long) nr * k / T), (int) ((long long) nr * (k + 1) / T));
+                gather(0, (int) ((long long) nr / T));
+                for (auto& x : th) x.join();
+            }
+            const size_t codes = (size_t) nr * n;
+            bytes_read += codes + codes / 16;
+            QW_CUDA(cudaMemcpyAsync(dq[b], hq, codes, cudaMemcpyHostToDevice, stream));
+            QW_CUDA(cudaMemcpyAsync(ds[b], hs, codes / 16, cudaMemcpyHostToDevice, stream));
+            launch_repack(dq[b], ds[b], n, 0, n, nr, dst, dst_row0 + r * dst_row_step, dst_row_step, stream);
+            QW_CUDA(cudaGetLastError());
+            QW_CUDA(cudaEventRecord(done[b], stream));
+            used[b] = true;
+        }
         return 0;
     }
 };
-
-// Upload rows [row0, row0+rows) of a [*, src_n] tensor and repack the column window
-// [col0, col0+n) into dst rows dst_row0 + r*dst_row_step.
-int put(Stage& st, const QwenCudaQ8& t, int src_n, int row0, int rows, int col0, int n, uint8_t* dst, int dst_row0,
-        int dst_row_step, cudaStream_t stream) {
-    const size_t codes = (size_t) rows * src_n;
-    if (st.reserve(codes)) return -1;
-    QW_CUDA(cudaMemcpyAsync(st.q, t.q + (size_t) row0 * src_n, codes, cudaMemcpyHostToDevice, stream));
-    QW_CUDA(cudaMemcpyAsync(st.s, t.s + (size_t) row0 * src_n / 64, codes / 64 * 4, cudaMemcpyHostToDevice, stream));
-    launch_repack(st.q, st.s, src_n, col0, n, rows, dst, dst_row0, dst_row_step, stream);
-    QW_CUDA(cudaGetLastError());
-    if (getenv("QWEN_CUDA_SYNC_UPLOAD")) QW_CUDA(cudaStreamSynchronize(stream));
-    // the staging buffers are reused by the next tensor; pageable-source copies are
-    // already synchronous with respect to the host buffer, the kernel is stream ordered
-    return 0;
-}
 
 } // namespace
 
@@ -142,24 +187,26 @@ extern "C" QwenCudaCtx* qwen_cuda_create(const QwenCudaModelDesc* m, int device,
     c->bytes_weights = (c->w_qkv_stride + c->w_o_stride + c->w_13_stride + c->w_2_stride) * L + cls_bytes
                        + (emb_alias ? 0 : emb_bytes);
     {
-        Stage st;
+        Uploader up;
+        if (up.init()) return fail();
         cudaStream_t s = c->stream;
         for (int l = 0; l < L; ++l) {
             uint8_t* qkv = c->w_qkv + l * c->w_qkv_stride;
-            if (put(st, m->wq[l], D, r * Pl, Pl, 0, D, qkv, 0, 1, s) || put(st, m->wk[l], D, r * Kl, Kl, 0, D, qkv, Pl, 1, s)
-                || put(st, m->wv[l], D, r * Kl, Kl, 0, D, qkv, Pl + Kl, 1, s)
-                || put(st, m->wo[l], P, 0, D, r * Pl, Pl, c->w_o + l * c->w_o_stride, 0, 1, s)
-                || put(st, m->w1[l], D, r * Hdl, Hdl, 0, D, c->w_13 + l * c->w_13_stride, 0, 2, s)
-                || put(st, m->w3[l], D, r * Hdl, Hdl, 0, D, c->w_13 + l * c->w_13_stride, 1, 2, s)
-                || put(st, m->w2[l], c->Hd, 0, D, r * Hdl, Hdl, c->w_2 + l * c->w_2_stride, 0, 1, s))
+            if (up.put(m->wq[l], D, r * Pl, Pl, 0, D, qkv, 0, 1, s) || up.put(m->wk[l], D, r * Kl, Kl, 0, D, qkv, Pl, 1, s)
+                || up.put(m->wv[l], D, r * Kl, Kl, 0, D, qkv, Pl + Kl, 1, s)
+                || up.put(m->wo[l], P, 0, D, r * Pl, Pl, c->w_o + l * c->w_o_stride, 0, 1, s)
+                || up.put(m->w1[l], D, r * Hdl, Hdl, 0, D, c->w_13 + l * c->w_13_stride, 0, 2, s)
+                || up.put(m->w3[l], D, r * Hdl, Hdl, 0, D, c->w_13 + l * c->w_13_stride, 1, 2, s)
+                || up.put(m->w2[l], c->Hd, 0, D, r * Hdl, Hdl, c->w_2 + l * c->w_2_stride, 0, 1, s))
                 return fail();
         }
-        if (put(st, m->cls, D, r * Vl, Vl, 0, D, c->w_cls, 0, 1, s)) return fail();
-        if (!emb_alias && put(st, m->emb, D, 0, c->V, 0, D, c->w_emb, 0, 1, s)) return fail();
+        if (up.put(m->cls, D, r * Vl, Vl, 0, D, c->w_cls, 0, 1, s)) return fail();
+        if (!emb_alias && up.put(m->emb, D, 0, c->V, 0, D, c->w_emb, 0, 1, s)) return fail();
         if (cudaStreamSynchronize(s) != cudaSuccess) {
             qw_set_error("qwen_cuda_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
             return fail();
         }
+        c->bytes_read = up.bytes_read;
         (void) K;
     }
     if (upload_f32(&c->att_norm, m->att_rms_norm, (size_t) L * D) || upload_f32(&c->ffn_norm, m->ffn_rms_norm, (size_t) L * D)
@@ -245,11 +292,9 @@ extern "C" void qwen_cuda_host_free(void* p) {
 
 int qw_mega_profile_enable(QwenCudaCtx* c);
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems);
-int qw_mega_tlog(QwenCudaCtx* c, int warp, unsigned long long* host);
 int qw_mega_reset(QwenCudaCtx* c);
 bool qw_mega_tp_ready(const QwenCudaCtx* c);
 const float* qw_mega_debug_ptr(QwenCudaCtx* c, const char* what);
-extern "C" int qwen_cuda_debug_tile_log(QwenCudaCtx* c, int warp, unsigned long long* host) { return c ? qw_mega_tlog(c, warp, host) : -2; }
 extern "C" int qwen_cuda_debug_profile_enable(QwenCudaCtx* c) { return c ? qw_mega_profile_enable(c) : -2; }
 extern "C" int qwen_cuda_debug_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
     return c ? qw_mega_profile_read(c, host, max_elems) : -2;
@@ -351,6 +396,16 @@ extern "C" int qwen_cuda_set_path(QwenCudaCtx* c, int path) {
 
 extern "C" int qwen_cuda_get_path(const QwenCudaCtx* c) { return c ? c->path : -2; }
 
+// What this context (= this tensor-parallel rank) holds in HBM and what it read from the checkpoint at create.
+extern "C" int qwen_cuda_memory(const QwenCudaCtx* c, size_t* weight_bytes, size_t* kv_bytes, size_t* read_bytes) {
+    if (!c) return -2;
+    if (weight_bytes) *weight_bytes = c->bytes_weights;
+    if (kv_bytes) *kv_bytes = c->bytes_kv;
+    if (read_bytes) *read_bytes = c->bytes_read;
+    return 0;
+}
+
+static int qw_check_flag(QwenCudaCtx* c);
 static int step(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     if (pos < 0 || pos >= c->S) {
         qw_set_error("forward: pos %d outside [0, %d)", pos, c->S);
@@ -360,12 +415,21 @@ static int step(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         qw_set_error("forward: token %d outside [0, %d)", token, c->V);
         return -2;
     }
+    if (c->tp_size > 1 && *(volatile int*) c->err_flag) return qw_check_flag(c); // sticky (see qw_check_flag)
     return c->path == 1 ? qw_decode_ops(c, token, token_dev, pos) : qw_decode_mega(c, token, token_dev, pos);
 }
 
 static int qw_check_flag(QwenCudaCtx* c) {
     const int flag = *(volatile int*) c->err_flag;
     if (flag) {
+        if (c->tp_size > 1) {
+            // Tensor parallel: the peers store into this rank's arenas (and this rank into theirs) -- a rank-local refill would
+            // race with them, and the ranks would disagree on which arena the next launch uses. The group stays in a STICKY
+            // error state: every later step of this context fails with the same code; recovery = destroy all ranks' contexts.
+            qw_set_error("decode kernel reported error %d on tensor-parallel rank %d (a wait timed out); the context is unusable", flag,
+                         c->tp_rank);
+            return -3;
+        }
         qw_set_error("decode kernel reported error %d (a wait inside the persistent kernel timed out)", flag);
         *c->err_flag = 0;
         qw_mega_reset(c); // the flow arenas are meaningless after an abort

@@ -715,8 +715,10 @@ __device__ __forceinline__ void consume_mat(const Shared& sh, const MegaParams& 
         }
     } else if (TP && KIND == 3) {
         __threadfence_system();
+        bar_consumers(); // the next prologue rewrites sh.xq: no warp may still be reading it (the staged branch has its barrier)
     } else {
         flush_stores();
+        bar_consumers();
     }
 #ifdef QW_UNITPROF
     UP_END(up_store);
@@ -1634,6 +1636,7 @@ int qw_mega_init(QwenCudaCtx* c) {
     return qw_mega_reset(c);
 }
 
+// (Cross-rank ordering of the arena reuse: see the invariant at the logits all-gather in qw_decode_mega.)
 // Tensor parallelism, one process per GPU: exchange cudaIpc handles of the two flow arenas through the NCCL
 // communicator and map every peer's arenas into this process (NVLink peer access). After this the persistent
 // kernel's wo / w2 epilogues store their partial sums straight into every rank's arena -- the all-reduce is part
@@ -1786,7 +1789,13 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
         QW_CUDA(cudaLaunchCooperativeKernel(decode_kernel(p.kv_mul, c->tp_size > 1), dim3(st->grid), dim3(kThreads), args, st->smem, c->stream));
     st->last_layers = p.layers_run;
     ++st->launches;
-    // the classifier is split over vocabulary rows: gather the logits slices
+    // The classifier is split over vocabulary rows: gather the logits slices.
+    // INVARIANT this collective also carries: rank A's launch N peer-stores into rank B's arena[N & 1], which B's launch
+    // N - 1 refilled with the sentinel. Nothing inside the kernels orders A's launch N after B's launch N - 1 -- the
+    // all-gather enqueued after EVERY launch does: it completes on A only once every rank has contributed the logits of
+    // its launch N - 1, i.e. has finished that kernel including its refill. A step variant without a collective after the
+    // launch (a per-rank argmax chain, a no-logits step) would need its own cross-rank epoch exchange before the next
+    // launch. The arena parity (launches & 1) is per process: all ranks must run the same sequence of steps.
     if (c->tp_size > 1 && qw_tp_allgather(c, c->logits, c->logits_all, c->Vl)) return -1;
     return 0;
 }
@@ -1820,10 +1829,6 @@ int qw_mega_profile_enable(QwenCudaCtx* c) {
     QW_CUDA(cudaMemset(st->prof, 0, n * 8));
     QW_CUDA(cudaDeviceSynchronize());
     return (int) n;
-}
-int qw_mega_tlog(QwenCudaCtx*, int, unsigned long long*) {
-    qw_set_error("per-tile logging is not compiled into this build");
-    return -1;
 }
 int qw_mega_profile_read(QwenCudaCtx* c, unsigned long long* host, size_t max_elems) {
     MegaState* st = state_of(c);

@@ -254,6 +254,7 @@ __device__ __forceinline__ void pw_consume_mat(const Shared& sh, const MegaParam
         }
     } else {
         flush_stores();
+        bar_consumers(); // the next prologue rewrites sh.xq: no warp may still be reading it (the staged branch has its barrier)
     }
 }
 

@@ -239,9 +239,13 @@ Model* model_create(const char* path, int override_seq_len) {
         qwen_cuda_set_path(ctx, 1);
     }
     mp->ctx = ctx;
-    const double kv_mb = 2.0 * L * (double) p->seq_len * K * sizeof(float) / (1024.0 * 1024.0);
-    fprintf(stderr, "[Weights] Uploaded %.2f MB to device\n", (double) st.st_size / (1024.0 * 1024.0));
-    fprintf(stderr, "[ForwardState] Allocated %.2f MB on device\n", kv_mb);
+    /* the reference's banners (src/model.c:277, 399), with what THIS process put on its device: under tensor parallelism a
+     * rank holds 1/tp of the matrices and of the KV cache */
+    size_t wb = 0, kvb = 0, rd = 0;
+    qwen_cuda_memory(ctx, &wb, &kvb, &rd);
+    fprintf(stderr, "[Weights] Uploaded %.2f MB to device\n", (double) wb / (1024.0 * 1024.0));
+    fprintf(stderr, "[ForwardState] Allocated %.2f MB on device\n", (double) kvb / (1024.0 * 1024.0));
+    (void) K;
     return m;
 
 fail_state:

@@ -13,7 +13,7 @@ print(" ".join(pkg.checkpoint.ensure_checkpoint("/tmp/tpck", n, seed=11) for n i
 PY
 )
 echo "checkpoints: $PATHS"
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/tp_gpu_worker.py $PATHS > gpurun_out/tp${N}_worker.log 2>&1
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/tp_gpu_worker.py $PATHS > gpurun_out/tp${N}_worker.log 2>&1; cp gpurun_out/tp${N}_worker.log gpurun_out/r2_tp${N}_worker.log
 echo "worker rc=$?"; grep -E "TP_GPU_OK|Error|assert" gpurun_out/tp${N}_worker.log | head -5
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 128 --warmup 8 > gpurun_out/bench_tp${N}.json 2> gpurun_out/bench_tp${N}.err
 echo "bench rc=$?"; cat gpurun_out/bench_tp${N}.json; tail -2 gpurun_out/bench_tp${N}.err
