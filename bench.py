@@ -40,6 +40,7 @@ CKPT_DIR = os.environ.get("QWEN3_B200_CKPT_DIR", "/tmp/qwen3_b200_ckpt")
 WORKLOADS = {
     "4b-decode-ctx4096": ("4b", 4096),
     "8b-decode-ctx4096": ("8b", 4096),
+    "32b-decode-ctx32k": ("32b", 32600),   # BASELINE config 5 (TP=8): decode near the reference's 32768-position cap
     "1.7b-decode-ctx512": ("1.7b", 512),
     "0.6b-decode-ctx128": ("0.6b", 128),
     "small-decode-ctx128": ("small", 128),
@@ -222,6 +223,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tp-base", action="store_true", help="skip the 8B one-GPU figure on the N=1 line")
+    ap.add_argument("--no-tp1", action="store_true", help="N > 1: skip the same-workload one-GPU leg")
     ap.add_argument("--path", default="mega", choices=["mega", "ops"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

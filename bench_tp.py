@@ -61,13 +61,39 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
             raise SystemExit("forward failed: " + ql.err())
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
+    # prompt prefill under tensor parallelism (tcgen05 GEMMs per rank + ncclAllReduce of the [T][dim] partial sums): config 5
+    # asks for 2048 tokens, the other workloads time 512; best of 2 after one warm-up pass
+    prefill = None
+    try:
+        Tp = 2048 if shape_name == "32b" else 512
+        toks = [int(t) for t in np.random.default_rng(0).integers(0, shape.vocab_size, size=Tp)]
+        gm.prefill_nocopy(toks, 0)
+        best = 1e9
+        for _ in range(2):
+            dist.barrier()
+            t0 = time.perf_counter()
+            if not gm.prefill_nocopy(toks, 0):
+                raise RuntimeError("prefill failed: " + ql.err())
+            best = min(best, max_over_ranks(time.perf_counter() - t0))
+        macs = Tp * (shape.weight_elements() - shape.vocab_size * shape.dim)
+        prefill = {"workload": f"{shape_name}-prefill{Tp}-tp{world}", "tok_s": Tp / best, "ms": 1e3 * best,
+                   "int8_tops_all_gpus": 2 * macs / best / 1e12}
+    except Exception as e:
+        prefill = {"error": repr(e)}
     gm.close()
     dist.barrier()
+    dist.destroy_process_group()  # the other ranks leave now: nothing of theirs may spin beside the one-GPU and CPU legs
+    if rank != 0:
+        return 0
     if rank == 0:
         # the same workload on ONE GPU, measured now on rank 0's device: the base of the scaling curve
         os.environ.pop("QWEN_CUDA_TP_RANK", None)
         os.environ.pop("QWEN_CUDA_TP_SIZE", None)
         try:
+            if args.no_tp1:
+                raise RuntimeError("skipped (--no-tp1)")
+            if shape.weight_elements() * 17 / 16 + 2 * 4 * shape.n_layers * seq_len * shape.kv_dim > 150e9:
+                raise RuntimeError("does not fit one GPU's 180 GB with its KV cache")
             tp1 = single_gpu_decode(pkg, ql, shape_name, ctx, K, W)
         except Exception as e:
             tp1 = {"error": repr(e)}
@@ -87,6 +113,7 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
         line["config"]["parallelism"] = f"tp{world}"
         line["config"]["path"] = "mega+peer-stores" if fused else "ops+nccl"
         line["model_create_s"] = model_create_s
+        line["prefill"] = prefill
         line["tp1_same_workload"] = tp1
         if "value" in tp1:
             line["vs_tp1_same_workload"] = tok_s / tp1["value"]
@@ -98,6 +125,4 @@ def run(args, base, pkg, shape, shape_name, ctx, K, W, rank, world):
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
     return 0

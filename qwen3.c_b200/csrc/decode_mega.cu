@@ -1563,8 +1563,11 @@ int qw_mega_init(QwenCudaCtx* c) {
     // shallower prefetch costs. QWEN_MEGA_NSLOT overrides (up to what fits).
     // Single-GPU contexts run the per-warp streaming variant (decode_pw.cuh) when its 15 warp regions fit beside the
     // activation vector; QWEN_MEGA_PW=0 selects the ring variant (the kernel of tensor-parallel contexts).
-    st->pw = c->tp_size == 1 && avail >= kConsumerWarps * kPwRegion && qw_sg_per_row(c->D) >= 1;
-    if (const char* e = getenv("QWEN_MEGA_PW")) st->pw = st->pw && atoi(e) != 0;
+    // ... and when a row of the dim-column matrices (wq|wk|wv, w1/w3, classifier: most of the bytes) is ONE chunk, so that a
+    // row pair travels as one 5 KB copy; with two copies per item the issue server saturates (measured: 8B shape 388 tok/s
+    // against 420 with the ring variant, 4B 570 against 535).
+    st->pw = c->tp_size == 1 && avail >= kConsumerWarps * kPwRegion && qw_sg_per_row(c->D) <= kPwChunkRecs;
+    if (const char* e = getenv("QWEN_MEGA_PW")) st->pw = atoi(e) != 0 && c->tp_size == 1 && avail >= kConsumerWarps * kPwRegion;
     const int fit = std::min(kMaxSlots, avail / kSlotBytes);
     st->nslot = std::min(fit, 5);
     if (const char* e = getenv("QWEN_MEGA_NSLOT")) st->nslot = std::max(2, std::min(fit, atoi(e)));
