@@ -1743,14 +1743,17 @@ int qw_decode_mega(QwenCudaCtx* c, int token, const int* token_dev, int pos) {
     p.dbg_stride = (int) c->dbg_codes_stride;
     int stage_env = 1; // QWEN_MEGA_STAGE=0: per-warp stores + fence instead of the staged bulk store
     if (const char* e = getenv("QWEN_MEGA_STAGE")) stage_env = atoi(e);
+    int stage_mask = 31; // QWEN_MEGA_STAGE_MASK: bit k = matrix k (0 qkv, 1 wo, 2 w1/w3, 3 w2, 4 classifier) uses the staged store
+    if (const char* e = getenv("QWEN_MEGA_STAGE_MASK")) stage_mask = atoi(e);
+    int mat_index = 0;
     const int grid = st->grid;
-    auto desc = [stage_env, grid](const uint8_t* base, size_t stride, int rows, int n, int kind) {
+    auto desc = [stage_env, stage_mask, &mat_index, grid](const uint8_t* base, size_t stride, int rows, int n, int kind) {
         int rt = kSlotBytes / (int) qw_row_bytes(n);
         if (rt >= 2) rt &= ~1; // whole 2-row units per tile
         if (rt < 2 && kind == 2) rt = 2;
         // staged bulk store: a CTA's slice of the output must start and end on 16 bytes (4 rows; 8 for the w1/w3 pairs)
         const int sg = kind == 2 ? 8 : 4;
-        const bool stage = stage_env && rows % sg == 0 && (rows / sg / grid + 1) * sg <= (kind == 2 ? 2048 : kScrFloats); // kind 2: raw sums wait at +2048 (decode_pw.cuh)
+        const bool stage = stage_env && ((stage_mask >> mat_index++) & 1) && rows % sg == 0 && (rows / sg / grid + 1) * sg <= (kind == 2 ? 2048 : kScrFloats); // kind 2: raw sums wait at +2048 (decode_pw.cuh)
         const int gran = stage ? sg : (kind == 2 ? 2 : 1);
         const int recs = qw_sg_per_row(n), C = (recs + kPwChunkRecs - 1) / kPwChunkRecs, cr = (recs + C - 1) / C;
         return MatDesc{base, stride, rows, n, gran, rt, stage ? 1 : 0, C, cr, kind};
