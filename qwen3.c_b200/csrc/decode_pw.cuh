@@ -9,11 +9,12 @@
 // of a group of four fill the whole ring, so the next group's KV rows are requested only when the group is done, and a w2
 // row pair fills a slot, so only `ring depth` warps have work at a time.
 //
-// Here every warp is its own pipeline: it owns 12 KB of shared memory and three mbarriers that nobody else waits on,
-// issues its own TMA bulk copies (one elected lane), and walks only its own work:
+// Here every warp is its own pipeline: it owns 12 KB of shared memory and three mbarriers that nobody else waits on
+// and walks only its own work. Weight copies are issued FOR it by the issue server (warp 15, see PwCtl below); KV copies
+// by one elected lane of the warp itself:
 //   * GEMV phases: work unit = 2 rows; a row is cut into chunks of <= 11 records (2992 B) so that two stages of
 //     [row a chunk | row b chunk] fit the region; the lane partial sums ride across a unit's chunks. After consuming a
-//     stage the warp refills it with its NEXT item -- across phase boundaries: weights do not depend on activations, so a
+//     stage the warp publishes a counter and the server refills it with the warp's NEXT item -- across phase boundaries: weights do not depend on activations, so a
 //     warp waiting at a hand-off already has its first two items of the next matrix in flight (15 x 12 KB per SM).
 //   * attention: the warps of a head group split the CTA's cached positions to the position; a warp streams blocks of 8
 //     positions as [8 K rows] and [8 V rows] items through three 4 KB sub-stages; the K rows' sub-stage is handed back
