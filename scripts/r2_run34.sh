@@ -1,0 +1,10 @@
+cd $GRAFT_REPO_ROOT
+O=gpurun_out/r2_run34.log; : > $O
+run() { timeout 200 python scripts/quick_decode.py 4b 4096 64 2>&1 | tail -1 | sed "s/^/$1: /" >> $O; }
+QWEN_MEGA_L2MODE=0 run "bulk prefetch only"
+QWEN_MEGA_L2MODE=1 run "consumer touches"
+QWEN_MEGA_L2MODE=2 run "both"
+QWEN_MEGA_L2MODE=1 timeout 200 python scripts/phase_profile.py 4b 4096 2>&1 | grep -v "^\[" | grep -v skew >> $O
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "golden_micro or logits_and_kv or real_layer or deterministic or greedy_256 or staged" 2>&1 | tail -3 >> $O
+QWEN_MEGA_L2MODE=1 timeout 200 python scripts/quick_decode.py 1.7b 512 64 2>&1 | tail -1 >> $O
+QWEN_MEGA_L2MODE=1 timeout 200 python scripts/quick_decode.py 0.6b 128 64 2>&1 | tail -1 >> $O

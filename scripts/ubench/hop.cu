@@ -19,7 +19,7 @@ __device__ __forceinline__ uint4 load_u4(const void* p) {
     return v;
 }
 __device__ __forceinline__ bool unset(const uint4& v) { return v.x == kSent || v.y == kSent || v.z == kSent || v.w == kSent; }
-template <int PUB, int WORK>
+template <int PUB, int WORK, int SKEW = 0, int POLL = 0>
 __global__ void __launch_bounds__(480, 1) k_hop(uint32_t* arena, int D, int hops, unsigned long long* out, float* sink) {
     __shared__ __align__(16) float stage[64];
     __shared__ float red[16];
@@ -29,13 +29,30 @@ __global__ void __launch_bounds__(480, 1) k_hop(uint32_t* arena, int D, int hops
     const unsigned long long t0 = gtime();
     for (int h = 0; h < hops; ++h) {
         uint32_t* vec = arena + (size_t) h * D;
+        if (SKEW) { // emulate load imbalance: every CTA is late by a pseudo-random 0 .. SKEW cycles
+            const unsigned r = ((unsigned) b * 2654435761u + (unsigned) h * 40503u) >> 7;
+            const long long until = clock64() + (long long) (r % (unsigned) SKEW);
+            while (clock64() < until) {}
+        }
         // produce
-        if (PUB == 0) {
+        if (PUB == 0 || PUB >= 4) {
+            // PUB 4: no fence at all (every word validates itself) | 5: red.xor against the sentinel, no fence | 6: fence.cta only
+            // PUB 7: as 0 plus a CTA barrier before the poll | 8: only the storing warps fence | 9: no fence, nanosleep(400) before the poll
+            bool stored = false;
             for (int u = warp; 2 * u < r1 - r0; u += 15) {
                 const int row = r0 + 2 * u + lane;
-                if (lane < 2 && row < r1) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(vec + row), "r"(__float_as_uint(acc + (float) row)) : "memory");
+                stored = true;
+                if (lane < 2 && row < r1) {
+                    const uint32_t val = __float_as_uint(acc + (float) row);
+                    if (PUB == 5) asm volatile("red.relaxed.gpu.global.xor.b32 [%0], %1;" ::"l"(vec + row), "r"(val ^ kSent) : "memory");
+                    else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(vec + row), "r"(val) : "memory");
+                }
             }
-            __threadfence();
+            if (PUB == 0 || PUB == 7) __threadfence();
+            if (PUB == 6) __threadfence_block();
+            if (PUB == 8 && stored) __threadfence();
+            if (PUB == 7) asm volatile("bar.sync 1, 480;" ::: "memory");
+            if (PUB == 9) __nanosleep(400);
         } else {
             for (int u = warp; 2 * u < r1 - r0; u += 15) {
                 const int row = r0 + 2 * u + lane;
@@ -63,6 +80,7 @@ __global__ void __launch_bounds__(480, 1) k_hop(uint32_t* arena, int D, int hops
             const uint32_t* q = vec + warp * 256 + lane * 8;
             uint4 a = load_u4(q), c = load_u4(q + 4);
             while (unset(a) || unset(c)) {
+                if (POLL) __nanosleep(POLL);
                 if (unset(a)) a = load_u4(q);
                 if (unset(c)) c = load_u4(q + 4);
             }
@@ -94,13 +112,13 @@ __global__ void __launch_bounds__(480, 1) k_hop(uint32_t* arena, int D, int hops
 __global__ void k_fill(uint32_t* p, size_t n, uint32_t v) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
 }
-template <int PUB, int WORK>
+template <int PUB, int WORK, int SKEW = 0, int POLL = 0>
 void run(const char* name, uint32_t* arena, unsigned long long* out, float* sink, int D) {
     const int hops = 64, G = 148;
     for (int rep = 0; rep < 2; ++rep) {
         k_fill<<<148, 256>>>(arena, (size_t) hops * D, kSent);
         void* args[] = {&arena, (void*) &D, (void*) &hops, &out, &sink};
-        cudaLaunchCooperativeKernel((const void*) k_hop<PUB, WORK>, dim3(G), dim3(480), args, 0, 0);
+        cudaLaunchCooperativeKernel((const void*) k_hop<PUB, WORK, SKEW, POLL>, dim3(G), dim3(480), args, 0, 0);
         cudaError_t e = cudaDeviceSynchronize();
         if (e) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
     }
@@ -117,8 +135,34 @@ int main() {
     run<1, 0>("staged, barrier, ONE TMA bulk store, poll only", arena, out, sink, D);
     run<2, 0>("staged, barrier, warp 0 st.relaxed + fence, poll only", arena, out, sink, D);
     run<3, 0>("staged, barrier, warp 0 st.release, poll only", arena, out, sink, D);
+    run<4, 0>("per-warp st.relaxed, NO fence, poll only", arena, out, sink, D);
+    run<5, 0>("per-warp red.xor vs sentinel, no fence, poll only", arena, out, sink, D);
+    run<6, 0>("per-warp st.relaxed + fence.cta, poll only", arena, out, sink, D);
+    run<7, 0>("per-warp st.relaxed + __threadfence + CTA barrier, poll only", arena, out, sink, D);
+    run<8, 0>("per-warp st.relaxed, only storing warps fence, poll only", arena, out, sink, D);
+    run<9, 0>("per-warp st.relaxed, no fence, nanosleep 400 before poll", arena, out, sink, D);
     run<0, 1>("per-warp st.relaxed + __threadfence, + norm + quant work", arena, out, sink, D);
+    run<4, 1>("per-warp st.relaxed, NO fence, + norm + quant work", arena, out, sink, D);
+    run<5, 1>("per-warp red.xor, no fence, + norm + quant work", arena, out, sink, D);
     run<1, 1>("staged, barrier, ONE TMA bulk store, + norm + quant work", arena, out, sink, D);
     run<2, 1>("staged, barrier, warp 0 st.relaxed + fence, + norm + quant work", arena, out, sink, D);
+    // load imbalance (every CTA late by 0 .. 3000 cycles = 0 .. 1.5 us per hop) and back-off between poll rounds
+    run<0, 1, 3000, 0>("skew 3000: per-warp st + fence, tight poll", arena, out, sink, D);
+    run<0, 1, 3000, 100>("skew 3000: per-warp st + fence, nanosleep 100", arena, out, sink, D);
+    run<0, 1, 3000, 300>("skew 3000: per-warp st + fence, nanosleep 300", arena, out, sink, D);
+    run<4, 1, 3000, 0>("skew 3000: per-warp st no fence, tight poll", arena, out, sink, D);
+    run<4, 1, 3000, 100>("skew 3000: per-warp st no fence, nanosleep 100", arena, out, sink, D);
+    run<4, 1, 3000, 200>("skew 3000: per-warp st no fence, nanosleep 200", arena, out, sink, D);
+    run<4, 1, 3000, 400>("skew 3000: per-warp st no fence, nanosleep 400", arena, out, sink, D);
+    run<4, 1, 3000, 800>("skew 3000: per-warp st no fence, nanosleep 800", arena, out, sink, D);
+    run<1, 1, 3000, 0>("skew 3000: staged bulk store, tight poll", arena, out, sink, D);
+    run<1, 1, 3000, 100>("skew 3000: staged bulk store, nanosleep 100", arena, out, sink, D);
+    run<1, 1, 3000, 200>("skew 3000: staged bulk store, nanosleep 200", arena, out, sink, D);
+    run<1, 1, 3000, 400>("skew 3000: staged bulk store, nanosleep 400", arena, out, sink, D);
+    run<1, 1, 0, 200>("no skew: staged bulk store, nanosleep 200", arena, out, sink, D);
+    run<1, 1, 0, 400>("no skew: staged bulk store, nanosleep 400", arena, out, sink, D);
+    run<4, 1, 0, 200>("no skew: per-warp st no fence, nanosleep 200", arena, out, sink, D);
+    run<4, 1, 0, 400>("no skew: per-warp st no fence, nanosleep 400", arena, out, sink, D);
+    run<5, 1, 3000, 200>("skew 3000: per-warp red.xor no fence, nanosleep 200", arena, out, sink, D);
     return 0;
 }
