@@ -26,6 +26,9 @@
 // promotion arithmetic (skipping it: 96 us) and the MMAs themselves are free (not issuing them: -7 %). Deeper
 // TMEM / shared-memory pipelines (2 -> 4 accumulators, 6 -> 12 stages), 128-byte SWIZZLE_128B operand rows
 // (two groups per stage) and prefetching the weight scales changed nothing or lost a few per cent.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -150,6 +153,19 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
 }
 __device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// (float) v for |v| < 2^22 without I2F: the integer is added to the bit pattern of 1.5 * 2^23 on the integer pipe, where one
+// ulp is 1, and the offset is taken off again by an exact fp32 subtraction. Two at a time. MEASURED SLOWER than I2FP in
+// k_prefill_gemm_p (a 16-output chunk 400-450 cycles against 300-350: VIADD + FADD2 cost more than the half-rate I2FP they
+// replace; the pipes do not overlap, a chunk costs the SUM of its instructions' cycles). Kept for the record, unused.
+__device__ __forceinline__ unsigned long long cvt2_exact(int a, int b) {
+    return add2(pack2(__int_as_float(a + 0x4B400000), __int_as_float(b + 0x4B400000)), pack2(-12582912.0f, -12582912.0f));
 }
 
 struct GemmParams {
@@ -295,6 +311,316 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
 }
 
+
+// =====================================================================================================================
+// k_prefill_gemm_p -- the persistent form (round 2). What the measurements said about the kernel above (QWEN_GEMM_DBG,
+// profiles/r2_prefill_gemm_components.log; scripts/ubench/tcrate.cu): with the TMA copies, the MMAs, the TMEM loads, the
+// scale loads AND the arithmetic all switched off, the 4B w1/w3 problem still takes 79 of its 143 us -- 608 one-tile CTAs in
+// 4.1 "waves" (the fifth holds 16 CTAs), each paying TMEM allocation, barrier set-up and an un-overlapped 64 KB output
+// store, and 34 mbarrier arrivals per group. TMEM itself is not the limit (tcgen05.ld: 386 B/clk/SM with 16 warps = 170
+// cycles for a 128 x 128 int32 tile), and the legacy register-accumulator path (mma.sync m16n8k32.s8) peaks at 1140 TOPS
+// before any epilogue. So the structure changed, not the instruction mix:
+//   * ONE CTA per SM walks a static list of tiles; TMEM and the barriers are set up once; the producer and the MMA issuer
+//     run ahead into the next tile while the epilogue warps store the finished one.
+//   * TOKENS are the UMMA M dimension (128 TMEM lanes = 128 tokens, one token per epilogue thread) and WEIGHT ROWS the N
+//     dimension, because N may be any multiple of 16 up to 256: the host picks N so that the tile count fills whole rounds
+//     of 148 SMs (4B, T = 512: w1/w3 N = 176 -> 444 tiles = 3 x 148; qkv N = 176 -> 140 tiles; wo / w2 N = 80 -> 128).
+//   * the activation scale of a token is a per-thread scalar (prefetched from the transposed scale matrix); the weight
+//     scales of the tile's rows arrive by TMA as a [N rows][4 groups] box once per 4 groups and every epilogue warp
+//     transposes its own columns into a private [4][64] table -> one broadcast LDS.128 per 4 outputs.
+//   * a shared-memory stage is released by the MMA's commit alone and an accumulator buffer by one arrival per warp:
+//     1 + 16 barrier arrivals per group instead of 34.
+// Arithmetic per output and group as above: ((float) dot * ws) * xs, added left to right in group order (bit-identical
+// to the reference matmul of every token).
+constexpr int kPM = 128;                       // tokens per tile
+constexpr int kPMaxN = 192;                    // weight rows per tile, at most (6 units of 8 columns per epilogue warp: 48 accumulators)
+constexpr int kPStages = 8;
+constexpr int kPABytes = kPM * 64;             // activation codes of one group: 128 tokens x 64 B
+constexpr int kPStageBytes = kPABytes + kPMaxN * 64; // 20 KB, keeps stages 1024-aligned
+constexpr int kPScSlots = 3;
+constexpr int kPScBytes = kPMaxN * 16;         // [N rows][4 scales]
+constexpr int kPEpiWarps = 16;
+constexpr int kPThreads = 32 * (2 + kPEpiWarps);
+constexpr int kPSmem = kPStages * kPStageBytes + kPScSlots * kPScBytes + kPEpiWarps * 4 * 64 * 4 + 1024;
+
+struct GemmPParams {
+    const float* xsT;      // [groups][Tpad]
+    float* out;            // [T][d]
+    int32_t* dots;         // optional [T][d][groups]
+    int d, n, T, Tpad;
+    int tok_tiles, tiles;  // tiles = row tiles x token tiles, token tile fastest (CTAs that run together share weight rows)
+    int* err;
+    long long* prof;       // QWEN_GEMM_PROF=1: clock64 stamps of CTA 0's first 64 groups, [3 roles][64][8] (normally NULL)
+};
+
+template <int U>
+__device__ __forceinline__ void tmem_ld_unit(uint32_t taddr, int (&v)[U]);
+template <>
+__device__ __forceinline__ void tmem_ld_unit<4>(uint32_t taddr, int (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_unit<8>(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// U = columns per tcgen05.ld (4 for N <= 128, 8 above), UC = loads per epilogue warp and group: N = 4 * UC * U weight rows per
+// tile, everything about the tile shape a compile-time constant (a first version with run-time unit counts spent more
+// issue slots on predicates and index arithmetic than on the promotion: 347 instructions per 48 outputs).
+template <int U, int UC, bool DOTS>
+__global__ void __launch_bounds__(kPThreads, 1)
+k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_s, const GemmPParams p) {
+    constexpr int N = 4 * UC * U;                 // weight rows per tile
+    constexpr int CW = UC * U;                    // columns per epilogue warp
+    constexpr uint32_t NBUF = 512 / N < 4 ? 512 / N : 4; // TMEM accumulator buffers
+    static_assert(N % 16 == 0 && N <= kPMaxN && CW <= 64, "tile shape");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sc_ring = smem + (size_t) kPStages * kPStageBytes;
+    float* wst_all = reinterpret_cast<float*>(sc_ring + kPScSlots * kPScBytes);
+    __shared__ __align__(8) uint64_t bars[2 * kPStages + 2 * kPScSlots + 2 * 4];
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int groups = p.n / 64;
+    const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kPStages]);
+    const uint32_t scfull0 = s_u32(&bars[2 * kPStages]), scempty0 = s_u32(&bars[2 * kPStages + kPScSlots]);
+    const uint32_t tfull0 = s_u32(&bars[2 * kPStages + 2 * kPScSlots]), tempty0 = tfull0 + 8 * 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPStages; ++s) {
+            mb_init(full0 + 8 * s, 1);
+            mb_init(empty0 + 8 * s, 1); // the MMAs that read the stage have retired
+        }
+        for (int s = 0; s < kPScSlots; ++s) {
+            mb_init(scfull0 + 8 * s, 1);
+            mb_init(scempty0 + 8 * s, kPEpiWarps);
+        }
+        for (int b = 0; b < 4; ++b) {
+            mb_init(tfull0 + 8 * b, 1);
+            mb_init(tempty0 + 8 * b, kPEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t it = 0, sc_it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.tiles && ok; tile += gridDim.x) {
+                const int row0 = (tile / p.tok_tiles) * N, t0 = (tile % p.tok_tiles) * kPM;
+                for (int g = 0; g < groups; ++g, ++it) {
+                    if ((g & 3) == 0) { // the weight scales of groups g .. g + 3: 16 bytes of every row of the tile
+                        const uint32_t sl = sc_it % kPScSlots;
+                        if (!(ok = mb_wait(scempty0 + 8 * sl, ((sc_it / kPScSlots) & 1) ^ 1, p.err, 5))) break;
+                        mb_expect(scfull0 + 8 * sl, (uint32_t) N * 16u);
+                        tma_2d(s_u32(sc_ring + sl * kPScBytes), &map_s, (g >> 2) * QW_SG_BYTES + 256, row0, scfull0 + 8 * sl);
+                        ++sc_it;
+                    }
+                    const uint32_t s = it % kPStages;
+                    long long* pr = (p.prof && blockIdx.x == 0 && it < 64) ? p.prof + (64 + it) * 8 : nullptr;
+                    if (pr) pr[0] = clock64();
+                    if (!(ok = mb_wait(empty0 + 8 * s, ((it / kPStages) & 1) ^ 1, p.err, 1))) break;
+                    if (pr) pr[1] = clock64();
+                    const uint32_t base = s_u32(smem + (size_t) s * kPStageBytes);
+                    mb_expect(full0 + 8 * s, (uint32_t) (kPABytes + N * 64));
+                    tma_2d(base, &map_x, g * 64, t0, full0 + 8 * s);
+                    tma_2d(base + kPABytes, &map_w, (g >> 2) * QW_SG_BYTES + (g & 3) * 64, row0, full0 + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_i8(kPM, N);
+            uint32_t it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.tiles && ok; tile += gridDim.x) {
+                for (int g = 0; g < groups; ++g, ++it) {
+                    const uint32_t s = it % kPStages, b = it % NBUF;
+                    long long* pr = (p.prof && blockIdx.x == 0 && it < 64) ? p.prof + it * 8 : nullptr;
+                    if (pr) pr[0] = clock64();
+                    if (!(ok = mb_wait(tempty0 + 8 * b, ((it / NBUF) & 1) ^ 1, p.err, 2))) break; // the epilogue has read this buffer
+                    if (pr) pr[1] = clock64();
+                    if (!(ok = mb_wait(full0 + 8 * s, (it / kPStages) & 1, p.err, 3))) break;      // operands landed
+                    if (pr) pr[2] = clock64();
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = s_u32(smem + (size_t) s * kPStageBytes);
+                    const uint32_t dcol = tmem_base + b * (uint32_t) N;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) // 64 codes = 2 x K32: D[token][row] (+)= X[token][k] * W[row][k]
+                        umma_i8(dcol, umma_desc_sw64(base + 32 * k), umma_desc_sw64(base + kPABytes + 32 * k), idesc, k);
+                    umma_commit(empty0 + 8 * s);
+                    umma_commit(tfull0 + 8 * b);
+                    if (pr) pr[3] = clock64();
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: one token per thread, CW columns per warp
+        const int ew = warp - 2;
+        const int q = warp & 3, j = ew >> 2;             // TMEM lane quarter (hardware rule: CTA warp id % 4), column block
+        const int cbeg = j * CW;                         // this warp's columns of the tile
+        float* wst = wst_all + ew * 256;                 // [4 groups][64 columns]: the warp's weight scales, transposed
+        uint32_t it = 0, sc_it = 0;
+        bool ok = true;
+        float xc[4] = {0.f, 0.f, 0.f, 0.f}, xn[4] = {0.f, 0.f, 0.f, 0.f};
+        auto load_xs = [&](const float* col, bool live, int g0, float (&dst)[4]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = (live && g0 + k < groups) ? __ldg(col + (size_t) (g0 + k) * p.Tpad) : 0.0f;
+        };
+        for (int tile = blockIdx.x; tile < p.tiles && ok; tile += gridDim.x) {
+            const int row0 = (tile / p.tok_tiles) * N, t0 = (tile % p.tok_tiles) * kPM;
+            const int t = t0 + q * 32 + lane;
+            const bool t_ok = t < p.T;
+            const float* xsp = p.xsT + (t_ok ? t : 0);
+            float acc[CW];
+#pragma unroll
+            for (int c = 0; c < CW; ++c) acc[c] = 0.0f;
+            if (tile == (int) blockIdx.x) load_xs(xsp, t_ok, 0, xn);
+            for (int g = 0; g < groups; ++g, ++it) {
+                const int gk = g & 3;
+                long long* pr = (p.prof && blockIdx.x == 0 && it < 64 && warp == 2 && lane == 0) ? p.prof + (128 + it) * 8 : nullptr;
+                if (pr) pr[0] = clock64();
+                if (gk == 0) {
+                    // the token's activation scales of groups g .. g + 3 were requested four groups ago (the first touch of a
+                    // scale row is an HBM miss); now ask for the next four -- of this tile or of the CTA's next tile
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) xc[k] = xn[k];
+                    if (g + 4 < groups) {
+                        load_xs(xsp, t_ok, g + 4, xn);
+                    } else if (tile + (int) gridDim.x < p.tiles) {
+                        const int tn = ((tile + (int) gridDim.x) % p.tok_tiles) * kPM + q * 32 + lane;
+                        load_xs(p.xsT + (tn < p.T ? tn : 0), tn < p.T, 0, xn);
+                    }
+                    // new weight-scale box: keep this warp's columns, transposed, and hand the slot back
+                    const uint32_t sl = sc_it % kPScSlots;
+                    if (pr) pr[5] = clock64();
+                    if (!(ok = mb_wait(scfull0 + 8 * sl, (sc_it / kPScSlots) & 1, p.err, 6))) break;
+                    if (pr) pr[6] = clock64();
+                    const float* box = reinterpret_cast<const float*>(sc_ring + sl * kPScBytes) + cbeg * 4;
+                    __syncwarp(); // everybody is done with the previous table
+#pragma unroll
+                    for (int c0 = 0; c0 < CW; c0 += 32) {
+                        const int c = c0 + lane;
+                        if (CW % 32 == 0 || c < CW) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(box + c * 4);
+                            wst[c] = s4.x; wst[64 + c] = s4.y; wst[128 + c] = s4.z; wst[192 + c] = s4.w;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mb_arrive(scempty0 + 8 * sl);
+                    ++sc_it;
+                }
+                const float xsc = gk == 0 ? xc[0] : gk == 1 ? xc[1] : gk == 2 ? xc[2] : xc[3];
+                const uint32_t b = it % NBUF;
+                if (pr) pr[1] = clock64();
+                if (!(ok = mb_wait(tfull0 + 8 * b, (it / NBUF) & 1, p.err, 4))) break;
+                if (pr) pr[2] = clock64();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + b * (uint32_t) N + cbeg;
+                const float* wg = wst + gk * 64;
+                const unsigned long long xs2 = pack2(xsc, xsc);
+                // TMEM -> registers two loads (2 U columns) at a time, software-pipelined: the loads of chunk k + 1 are in flight
+                // while chunk k is promoted; the buffer goes back to the MMA issuer as soon as the last load has landed
+                constexpr int NCH = (UC + 1) / 2;
+                int v[2][2][U];
+                tmem_ld_unit<U>(taddr, v[0][0]);
+                if (1 < UC) tmem_ld_unit<U>(taddr + U, v[0][1]);
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (pr && k < 2) pr[3 + k] = clock64();
+                    if (k + 1 < NCH) {
+                        tmem_ld_unit<U>(taddr + (2 * k + 2) * U, v[(k + 1) & 1][0]);
+                        if (2 * k + 3 < UC) tmem_ld_unit<U>(taddr + (2 * k + 3) * U, v[(k + 1) & 1][1]);
+                    } else {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mb_arrive(tempty0 + 8 * b);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (2 * k + h < UC) {
+                            const int (&vv)[U] = v[k & 1][h];
+                            if (DOTS && t_ok) { // test hook: a separate instantiation, the product kernel carries no such code
+#pragma unroll
+                                for (int e = 0; e < U; ++e) {
+                                    const int row = row0 + cbeg + (2 * k + h) * U + e;
+                                    if (row < p.d) p.dots[((size_t) t * p.d + row) * groups + g] = vv[e];
+                                }
+                            }
+#pragma unroll
+                            for (int e = 0; e < U; e += 4) {
+                                const int c = (2 * k + h) * U + e;
+                                const float4 w4 = *reinterpret_cast<const float4*>(wg + c);
+                                float lo, hi; // two packed multiplies, scalar adds (see the note at mul2)
+                                unpack2(mul2(mul2(pack2((float) vv[e], (float) vv[e + 1]), pack2(w4.x, w4.y)), xs2), lo, hi);
+                                acc[c] = __fadd_rn(acc[c], lo);
+                                acc[c + 1] = __fadd_rn(acc[c + 1], hi);
+                                unpack2(mul2(mul2(pack2((float) vv[e + 2], (float) vv[e + 3]), pack2(w4.z, w4.w)), xs2), lo, hi);
+                                acc[c + 2] = __fadd_rn(acc[c + 2], lo);
+                                acc[c + 3] = __fadd_rn(acc[c + 3], hi);
+                            }
+                        }
+                    }
+                }
+                if (pr) pr[7] = clock64();
+            }
+            if (ok && t_ok) { // the tile is done: the stores overlap the next tile's main loop
+                float* orow = p.out + (size_t) t * p.d + row0 + cbeg;
+                if (row0 + cbeg + CW <= p.d && (p.d & 3) == 0) {
+#pragma unroll
+                    for (int c = 0; c < CW; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CW; ++c)
+                        if (row0 + cbeg + c < p.d) orow[c] = acc[c];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+typedef void (*GemmPKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmPParams);
+// weight rows per tile -> kernel: N = 16 .. 128 in steps of 16 (U = 4), 160 and 192 (U = 8)
+template <bool DOTS>
+GemmPKernel gemm_p_kernel(int N) {
+    switch (N) {
+        case 16: return k_prefill_gemm_p<4, 1, DOTS>;
+        case 32: return k_prefill_gemm_p<4, 2, DOTS>;
+        case 48: return k_prefill_gemm_p<4, 3, DOTS>;
+        case 64: return k_prefill_gemm_p<4, 4, DOTS>;
+        case 80: return k_prefill_gemm_p<4, 5, DOTS>;
+        case 96: return k_prefill_gemm_p<4, 6, DOTS>;
+        case 112: return k_prefill_gemm_p<4, 7, DOTS>;
+        case 128: return k_prefill_gemm_p<4, 8, DOTS>;
+        case 160: return k_prefill_gemm_p<8, 5, DOTS>;
+        case 192: return k_prefill_gemm_p<8, 6, DOTS>;
+        default: return nullptr;
+    }
+}
+constexpr int kPShapes[] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192};
+
 // Measured int8 tensor peak (MEASURED_PEAKS.json has no int8 figure, "the builder must measure it on the
 // box"): every CTA issues `iters` back-to-back tcgen05.mma.cta_group::1.kind::i8 M128 N256 K32 on resident shared-memory
 // operands into one TMEM accumulator -- no loads, no promotion, no epilogue. The operand bytes are whatever shared memory
@@ -346,7 +672,8 @@ EncodeTiled encode_fn() {
     return fn;
 }
 
-int make_map(CUtensorMap* m, const void* base, uint64_t row_bytes, uint64_t rows, uint32_t box_rows) {
+int make_map(CUtensorMap* m, const void* base, uint64_t row_bytes, uint64_t rows, uint32_t box_rows, uint32_t box_bytes = 64,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_64B) {
     EncodeTiled enc = encode_fn();
     if (!enc) {
         qw_set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -354,10 +681,10 @@ int make_map(CUtensorMap* m, const void* base, uint64_t row_bytes, uint64_t rows
     }
     const cuuint64_t dims[2] = {row_bytes, rows};
     const cuuint64_t strides[1] = {row_bytes};
-    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t box[2] = {box_bytes, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         qw_set_error("cuTensorMapEncodeTiled failed (%d) for %llu x %llu", (int) rc, (unsigned long long) row_bytes,
@@ -377,13 +704,85 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
         qw_set_error("prefill gemm: bad shape d=%d n=%d T=%d", d, n, T);
         return -2;
     }
-    CUtensorMap mw, mx;
-    static int sms = 0;
+    CUtensorMap mw, mx, ms;
+    static int sms = 0, variant = -1;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    if (variant < 0) {
+        const char* e = getenv("QWEN_GEMM_V"); // 1: the one-tile-per-CTA kernel of round 1; default: the persistent kernel
+        variant = e ? atoi(e) : 2;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms_out) {
+        QW_CUDA(cudaEventCreate(&e0));
+        QW_CUDA(cudaEventCreate(&e1));
+    }
+    if (variant != 1) {
+        // Persistent kernel: pick the weight rows per tile N that minimises rounds x (N + a per-group fixed cost worth ~24
+        // rows), rounds = ceil(tiles / SMs); ties go to the smaller N (more SMs busy).
+        const int tok_tiles = (T + kPM - 1) / kPM;
+        int bestN = 16;
+        long best = -1;
+        for (int N : kPShapes) {
+            const long tiles = (long) ((d + N - 1) / N) * tok_tiles, rounds = (tiles + sms - 1) / sms;
+            const long cost = rounds * (N + 24);
+            if (best < 0 || cost < best) {
+                best = cost;
+                bestN = N;
+            }
+        }
+        static int forceN = -1;
+        if (forceN < 0) {
+            const char* e = getenv("QWEN_GEMM_N");
+            forceN = e ? atoi(e) : 0;
+        }
+        const int N = forceN > 0 ? forceN : bestN;
+        GemmPKernel kern = dots ? gemm_p_kernel<true>(N) : gemm_p_kernel<false>(N);
+        if (!kern) {
+            qw_set_error("prefill gemm: no kernel for %d weight rows per tile", N);
+            return -2;
+        }
+        if (make_map(&mx, xq, (uint64_t) n, (uint64_t) T, kPM) || make_map(&mw, w, qw_row_bytes(n), (uint64_t) d, (uint32_t) N)
+            || make_map(&ms, w, qw_row_bytes(n), (uint64_t) d, (uint32_t) N, 16, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return -1;
+        static bool attr_p = false;
+        if (!attr_p) {
+            for (int n_ : kPShapes) {
+                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<false>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<true>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+            }
+            attr_p = true;
+        }
+        static long long* prof = nullptr;
+        static int want_prof = -1;
+        if (want_prof < 0) want_prof = getenv("QWEN_GEMM_PROF") ? 1 : 0;
+        if (want_prof == 1 && !prof) {
+            cudaMalloc((void**) &prof, 3 * 64 * 8 * 8);
+            cudaMemset(prof, 0, 3 * 64 * 8 * 8);
+        }
+        GemmPParams pp{xsT, out, dots, d, n, T, Tpad, tok_tiles, ((d + N - 1) / N) * tok_tiles, err_dev, want_prof == 1 ? prof : nullptr};
+        const int grid = std::min(sms, pp.tiles);
+        if (ms_out) QW_CUDA(cudaEventRecord(e0, st));
+        kern<<<grid, kPThreads, kPSmem, st>>>(mx, mw, ms, pp);
+        QW_CUDA(cudaGetLastError());
+        if (want_prof == 1) { // one dump per process: the first launch
+            want_prof = 2;
+            cudaStreamSynchronize(st);
+            static long long h[3 * 64 * 8];
+            cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+            const long long z = h[0];
+            fprintf(stderr, "[gemm prof] d=%d n=%d T=%d N=%d tiles=%d (cycles since the MMA issuer's first stamp)\n", d, n, T, N, pp.tiles);
+            for (int i = 0; i < 20; ++i) {
+                const long long *m = h + i * 8, *pd = h + (64 + i) * 8, *ep = h + (128 + i) * 8;
+                fprintf(stderr, "[gemm prof] g%02d mma top %6lld tempty %6lld full %6lld commit %6lld | prod top %6lld empty %6lld | epi top %6lld scales %6lld tfull %6lld ld0 %6lld ld1 %6lld | xs-done %6lld scfull %6lld | done %6lld\n",
+                        i, m[0] - z, m[1] - z, m[2] - z, m[3] - z, pd[0] - z, pd[1] - z, ep[0] - z, ep[1] - z, ep[2] - z, ep[3] - z,
+                        ep[4] ? ep[4] - z : 0, ep[5] ? ep[5] - z : 0, ep[6] ? ep[6] - z : 0, ep[7] - z);
+            }
+        }
+    } else {
     // 128-token tiles unless 64-token tiles finish sooner: time ~ waves x cost of one tile, and a 64-token tile costs
     // ~0.7 of a 128-token one (measured). E.g. 1.7B wo / w2 at T = 512: 64 wide tiles on 148 SMs vs 128 narrow ones
     // in one wave -> narrow; 4B w2: 80 wide tiles in one wave vs 160 narrow ones in two -> wide.
@@ -401,15 +800,11 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
     }
     GemmParams p{w, xsT, out, dots, d, n, T, Tpad, err_dev};
     const dim3 grid((d + kTileM - 1) / kTileM, (T + TN - 1) / TN);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ms_out) {
-        QW_CUDA(cudaEventCreate(&e0));
-        QW_CUDA(cudaEventCreate(&e1));
-        QW_CUDA(cudaEventRecord(e0, st));
-    }
+    if (ms_out) QW_CUDA(cudaEventRecord(e0, st));
     if (wide) k_prefill_gemm<128><<<grid, kThreadsG, smem, st>>>(mw, mx, p);
     else k_prefill_gemm<64><<<grid, kThreadsG, smem, st>>>(mw, mx, p);
     QW_CUDA(cudaGetLastError());
+    }
     if (ms_out) {
         QW_CUDA(cudaEventRecord(e1, st));
         QW_CUDA(cudaEventSynchronize(e1));
