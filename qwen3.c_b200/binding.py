@@ -116,6 +116,7 @@ class QwenLib:
         L.qwen_cuda_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
         L.qwen_cuda_matmul_group_dots.argtypes = [c_int32_p, c_int8_p, c_int8_p, C.c_int, C.c_int, C.c_int]
         L.qwen_cuda_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p]
+        L.qwen_cuda_debug_attn_prefill.argtypes = [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.qwen_cuda_matmul_batch.argtypes = [c_float_p, c_int32_p, c_int8_p, c_float_p, c_int8_p, c_float_p, C.c_int, C.c_int,
                                              C.c_int, C.c_int, c_float_p]
 
@@ -179,6 +180,16 @@ class QwenLib:
                                                  _i8(np.ascontiguousarray(xq)), _fp(np.ascontiguousarray(xs)), _i8(wq), _fp(ws),
                                                  n, d, T, reps, C.byref(ms)), "matmul_batch")
         return out, dots, ms.value
+
+    def attn_prefill(self, q, k, v, n_heads, n_kv_heads, pos0, variant=2):
+        """Chunk attention kernel on host data (test hook): q [T][n_heads][128], k / v [pos0 + T][n_kv_heads * 128]."""
+        q = np.ascontiguousarray(q, np.float32)
+        T = q.shape[0]
+        out = np.full(q.shape, np.nan, np.float32)
+        self._ok(self.lib.qwen_cuda_debug_attn_prefill(_fp(out), _fp(q), _fp(np.ascontiguousarray(k, np.float32)),
+                                                       _fp(np.ascontiguousarray(v, np.float32)), n_heads, n_kv_heads, pos0, T, variant),
+                 "debug_attn_prefill")
+        return out
 
     def quantize_fused(self, x):
         """The persistent decode kernel's fused quantiser on a host vector (test hook)."""

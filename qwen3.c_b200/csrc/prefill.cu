@@ -14,6 +14,8 @@
 // Chunks of kChunkTokens tokens bound the activation memory; chunk c attends over the cache rows of the
 // earlier chunks plus its own causal part.
 #include <algorithm>
+#include <cstring>
+#include <cstdlib>
 
 #include "attn_core.cuh"
 #include "common.cuh"
@@ -28,7 +30,7 @@ constexpr int kChunkTokens = 512;
 struct PrefillBufs {
     int cap = 0;          // tokens the buffers hold
     int* tokens = nullptr;
-    float *x = nullptr, *xb = nullptr, *qkv = nullptr, *q = nullptr, *att = nullptr, *h13 = nullptr;
+    float *x = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr, *q = nullptr, *att = nullptr, *h13 = nullptr;
     int8_t* q8 = nullptr; // [cap][maxn] activation codes of the GEMM at hand (row pitch = its n)
     float* xsT = nullptr; // [maxn / 64][cap] activation scales, transposed for the GEMM epilogue
     int* err = nullptr;
@@ -49,15 +51,25 @@ __global__ void k_embed_rows(float* __restrict__ x, const uint8_t* __restrict__ 
 // interleaved (w1, w3) pairs (forward.c:122-139; src then has 2n values per token), then the Q8_0
 // quantiser (q8.c:5-30) with the reference's exact arithmetic. Codes go to q8[t][n], scales transposed to
 // xsT[g][Tpad]. 256 threads; warp w handles groups w, w + 8, ...
+// add != nullptr (with w): the residual add of the previous block (forward.c:295-298, 335-338) is done here first,
+// x[t] += add[t] written back, instead of in a pass of its own.
 __global__ void __launch_bounds__(256)
-k_prep_quant(const float* __restrict__ src, const float* __restrict__ w, int8_t* __restrict__ q8, float* __restrict__ xsT,
-             int n, int Tpad, int swiglu) {
+k_prep_quant(float* __restrict__ src, const float* __restrict__ add, const float* __restrict__ w, int8_t* __restrict__ q8,
+             float* __restrict__ xsT, int n, int Tpad, int swiglu) {
     __shared__ float red[8];
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* s = src + (size_t) t * (swiglu ? 2 * n : n);
+    float* s = src + (size_t) t * (swiglu ? 2 * n : n);
     float r = 1.0f;
     if (w) {
         float ss = 0.0f;
+        if (add) {
+            const float* a = add + (size_t) t * n;
+            for (int i = tid; i < n; i += 256) {
+                const float v = __fadd_rn(s[i], a[i]);
+                s[i] = v; // re-read by other threads after the barrier below
+                ss = __fmaf_rn(v, v, ss);
+            }
+        } else
         for (int i = tid; i < n; i += 256) ss = __fmaf_rn(s[i], s[i], ss);
         ss = warp_sum(ss);
         if (lane == 0) red[warp] = ss;
@@ -188,6 +200,175 @@ k_attn_prefill(const float* __restrict__ q, const float* __restrict__ k_layer, c
     }
 }
 
+// ---- round 2: tiled causal attention for a chunk --------------------------------------------------------------------
+// k_attn_prefill above gives every query token a warp and runs the decode kernel's per-warp online-softmax step: 31 shuffles
+// per 32 scores, one LDS.128 per K row per warp -- 7.7 TFLOP/s on B200 (10 % of the fp32 peak; a third of the prefill time).
+// k_attn_prefill_t is the register-blocked form: one CTA = 64 query tokens of ONE head, 128 threads as 8 x 16; for every
+// tile of 64 cached positions (aligned to absolute position 0, so a prompt prefilled in several calls sees the same tiles)
+//   S = Q K^T : thread (ty, tx) owns rows 8 ty .. 8 ty + 7 x keys tx, tx + 16, tx + 32, tx + 48; per float4 of the head
+//               dimension 8 broadcast Q loads + 4 conflict-free K loads (row pitch 132 floats) feed 128 FMAs;
+//   softmax   : score / sqrtf(128), causal mask, row maximum and sum over the 16 tx lanes by xor shuffles, running
+//               maximum / sum / rescale per row (forward.c:156-181 in online form);
+//   O += P V  : P goes through shared memory (over the K tile); thread (ty, tx) owns the same 8 rows x dims 4 tx .. 4 tx + 3
+//               and 64 + 4 tx .. : per 4 keys 8 broadcast P loads + 8 V loads feed 256 FMAs.
+// fp32 throughout (the cache is fp32, as the reference's). The heaviest query tiles (latest positions) are launched first.
+constexpr int kTQ = 64, kTK = 64, kTKPitch = 132, kTPPitch = 68;
+constexpr int kTSmem = (kTQ * 128 + kTK * kTKPitch + kTK * 128) * 4; // Q | K (later P) | V = 99 328 B: two CTAs per SM
+
+__global__ void __launch_bounds__(128, 2)
+k_attn_prefill_t(const float* __restrict__ q, const float* __restrict__ k_layer, const float* __restrict__ v_layer,
+                 float* __restrict__ out, int Hl, int kv_mul, int S, int pos0, int T, int sms) {
+    extern __shared__ __align__(16) float tsm[];
+    float* sQ = tsm;
+    float* sK = tsm + kTQ * 128;
+    float* sP = sK; // the probabilities overwrite the K tile once every thread has its scores
+    float* sV = sK + kTK * kTKPitch;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // Work of a CTA grows with its query tile's position. CTAs b and b + #SMs share an SM when the whole grid is resident
+    // (2 per SM), so the first #SMs CTAs take the heaviest items in descending order and the rest the lightest in ascending
+    // order: heavy + light per SM (4B shape, T = 512: 9 tile-units on the busiest SM instead of 12, 7.8 would be perfect).
+    // Larger grids are simply heaviest-first (the hardware scheduler then balances).
+    const int nq = (T + kTQ - 1) / kTQ;
+    const int n_items = nq * Hl;
+    int rank = (int) blockIdx.x;
+    if (n_items <= 2 * sms && rank >= sms) rank = n_items - 1 - (rank - sms);
+    const int qt = nq - 1 - rank / Hl, h = rank % Hl, kvh = h / kv_mul;
+    const int t0 = qt * kTQ;
+    const int rows = min(kTQ, T - t0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < kTQ * 32; i += 128) {
+        const int r = i >> 5, c = (i & 31) * 4;
+        *reinterpret_cast<float4*>(sQ + r * 128 + c) = r < rows ? *reinterpret_cast<const float4*>(q + ((size_t) (t0 + r) * Hl + h) * 128 + c) : zero4;
+    }
+    const float* K = k_layer + (size_t) kvh * S * 128;
+    const float* V = v_layer + (size_t) kvh * S * 128;
+    const int last_pos = pos0 + t0 + rows - 1;        // last position any query of the tile sees
+    const int qpos0 = pos0 + t0 + ty * 8;              // position of this thread's first row
+    const float inv = sqrtf(128.0f);
+    float m[8], l[8], o[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        m[i] = -INFINITY;
+        l[i] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[i][e] = 0.0f;
+    }
+    for (int p0 = 0; p0 <= last_pos; p0 += kTK) {
+        const int nk = min(kTK, last_pos + 1 - p0);
+        __syncthreads(); // the previous tile's P and V have been consumed (first pass: Q is in place)
+        for (int i = tid; i < kTK * 32; i += 128) {
+            const int r = i >> 5, c = (i & 31) * 4;
+            if (r < nk) {
+                cp_async16(sK + r * kTKPitch + c, K + (size_t) (p0 + r) * 128 + c);
+                cp_async16(sV + r * 128 + c, V + (size_t) (p0 + r) * 128 + c);
+            } else { // rows nobody may see: zeros, not whatever the cache holds (0 * NaN would poison P V)
+                *reinterpret_cast<float4*>(sK + r * kTKPitch + c) = zero4;
+                *reinterpret_cast<float4*>(sV + r * 128 + c) = zero4;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // ---- S = Q K^T
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.0f;
+#pragma unroll 2
+        for (int d = 0; d < 128; d += 4) {
+            float4 kf[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kf[j] = *reinterpret_cast<const float4*>(sK + (tx + 16 * j) * kTKPitch + d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 qf = *reinterpret_cast<const float4*>(sQ + (ty * 8 + i) * 128 + d);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s[i][j] = __fmaf_rn(qf.x, kf[j].x, s[i][j]);
+                    s[i][j] = __fmaf_rn(qf.y, kf[j].y, s[i][j]);
+                    s[i][j] = __fmaf_rn(qf.z, kf[j].z, s[i][j]);
+                    s[i][j] = __fmaf_rn(qf.w, kf[j].w, s[i][j]);
+                }
+            }
+        }
+        // ---- scale, causal mask, online softmax per row (the 16 tx lanes of a row sit in one half-warp)
+        const bool diag = p0 + kTK - 1 > qpos0; // some key of the tile may lie beyond some row of this thread
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = __fdiv_rn(s[i][j], inv);
+                if (diag && p0 + tx + 16 * j > qpos0 + i) v = -INFINITY;
+                s[i][j] = v;
+                mx = fmaxf(mx, v);
+            }
+#pragma unroll
+            for (int ofs = 8; ofs > 0; ofs >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, ofs));
+            const float m_new = fmaxf(m[i], mx);
+            const float scl = (m[i] == -INFINITY) ? 0.0f : expf(__fsub_rn(m[i], m_new));
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float e = (s[i][j] == -INFINITY) ? 0.0f : expf(__fsub_rn(s[i][j], m_new));
+                s[i][j] = e;
+                sum = __fadd_rn(sum, e);
+            }
+#pragma unroll
+            for (int ofs = 8; ofs > 0; ofs >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, ofs));
+            m[i] = m_new;
+            l[i] = __fmaf_rn(l[i], scl, sum);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[i][e] = __fmul_rn(o[i][e], scl);
+        }
+        __syncthreads(); // every thread is done with the K tile
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sP[(ty * 8 + i) * kTPPitch + tx + 16 * j] = s[i][j];
+        __syncthreads();
+        // ---- O += P V
+        const int nk4 = (nk + 3) & ~3;
+#pragma unroll 2
+        for (int kk = 0; kk < nk4; kk += 4) {
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                va[c] = *reinterpret_cast<const float4*>(sV + (kk + c) * 128 + tx * 4);
+                vb[c] = *reinterpret_cast<const float4*>(sV + (kk + c) * 128 + 64 + tx * 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 pf = *reinterpret_cast<const float4*>(sP + (ty * 8 + i) * kTPPitch + kk);
+                const float pw[4] = {pf.x, pf.y, pf.z, pf.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    o[i][0] = __fmaf_rn(pw[c], va[c].x, o[i][0]);
+                    o[i][1] = __fmaf_rn(pw[c], va[c].y, o[i][1]);
+                    o[i][2] = __fmaf_rn(pw[c], va[c].z, o[i][2]);
+                    o[i][3] = __fmaf_rn(pw[c], va[c].w, o[i][3]);
+                    o[i][4] = __fmaf_rn(pw[c], vb[c].x, o[i][4]);
+                    o[i][5] = __fmaf_rn(pw[c], vb[c].y, o[i][5]);
+                    o[i][6] = __fmaf_rn(pw[c], vb[c].z, o[i][6]);
+                    o[i][7] = __fmaf_rn(pw[c], vb[c].w, o[i][7]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = ty * 8 + i;
+        if (r < rows) {
+            float* dst = out + ((size_t) (t0 + r) * Hl + h) * 128;
+            *reinterpret_cast<float4*>(dst + tx * 4) =
+                make_float4(__fdiv_rn(o[i][0], l[i]), __fdiv_rn(o[i][1], l[i]), __fdiv_rn(o[i][2], l[i]), __fdiv_rn(o[i][3], l[i]));
+            *reinterpret_cast<float4*>(dst + 64 + tx * 4) =
+                make_float4(__fdiv_rn(o[i][4], l[i]), __fdiv_rn(o[i][5], l[i]), __fdiv_rn(o[i][6], l[i]), __fdiv_rn(o[i][7], l[i]));
+        }
+    }
+}
+
 // residual add over a chunk (forward.c:295-298, 335-338)
 __global__ void k_add_rows(float* __restrict__ x, const float* __restrict__ y, size_t n) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,12 +380,13 @@ int ensure_bufs(QwenCudaCtx* c, PrefillBufs*& pb, int T) {
     if (pb->cap >= T) return 0;
     const int cap = (T + 127) / 128 * 128;
     const size_t maxn = (size_t) std::max(c->D, std::max(c->Pl, c->Hdl));
-    void* old[] = {pb->tokens, pb->x, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
+    void* old[] = {pb->tokens, pb->x, pb->xa, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
     for (void* o : old)
         if (o) cudaFree(o);
     *pb = PrefillBufs();
     QW_CUDA(cudaMalloc((void**) &pb->tokens, (size_t) cap * 4));
     QW_CUDA(cudaMalloc((void**) &pb->x, (size_t) cap * c->D * 4));
+    QW_CUDA(cudaMalloc((void**) &pb->xa, (size_t) cap * c->D * 4));
     QW_CUDA(cudaMalloc((void**) &pb->xb, (size_t) cap * c->D * 4));
     QW_CUDA(cudaMalloc((void**) &pb->qkv, (size_t) cap * (c->Pl + 2 * c->Kl) * 4));
     QW_CUDA(cudaMalloc((void**) &pb->q, (size_t) cap * c->Pl * 4));
@@ -218,6 +400,7 @@ int ensure_bufs(QwenCudaCtx* c, PrefillBufs*& pb, int T) {
     QW_CUDA(cudaFuncSetAttribute(k_attn_prefill<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     QW_CUDA(cudaFuncSetAttribute(k_attn_prefill<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     QW_CUDA(cudaFuncSetAttribute(k_attn_prefill<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    QW_CUDA(cudaFuncSetAttribute(k_attn_prefill_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
     pb->cap = cap;
     return 0;
 }
@@ -229,7 +412,7 @@ static PrefillBufs*& bufs_of(QwenCudaCtx* c) { return *reinterpret_cast<PrefillB
 void qw_prefill_free(QwenCudaCtx* c) {
     PrefillBufs* pb = bufs_of(c);
     if (!pb) return;
-    void* old[] = {pb->tokens, pb->x, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
+    void* old[] = {pb->tokens, pb->x, pb->xa, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
     for (void* o : old)
         if (o) cudaFree(o);
     delete pb;
@@ -250,12 +433,22 @@ static int prefill_chunk(QwenCudaCtx* c, PrefillBufs* pb, const int* tokens_host
     for (int l = 0; l < c->L; ++l) {
         const size_t loff = (size_t) l * c->KVHl * c->S * 128;
         // attention block (forward.c:254-298)
-        k_prep_quant<<<T, 256, 0, st>>>(pb->x, c->att_norm + (size_t) l * D, pb->q8, pb->xsT, D, Tpad, 0);
+        // the previous layer's w2 output (all-reduced under tensor parallelism) joins the residual stream inside this pass
+        k_prep_quant<<<T, 256, 0, st>>>(pb->x, l > 0 ? pb->xb : nullptr, c->att_norm + (size_t) l * D, pb->q8, pb->xsT, D, Tpad, 0);
         if (gemm(c->w_qkv + l * c->w_qkv_stride, pb->qkv, Pl + 2 * Kl, D)) return -1;
         k_qkv_post_rows<<<dim3(T, c->Hl + 2 * c->KVHl), 128, 0, st>>>(pb->qkv, pb->q, c->k_cache + loff, c->v_cache + loff,
                                                                      c->q_norm + (size_t) l * 128, c->k_norm + (size_t) l * 128,
                                                                      c->rope_cos, c->rope_sin, c->Hl, c->KVHl, c->S, pos0);
+        static int attn_v = -1;
+        if (attn_v < 0) {
+            const char* e = getenv("QWEN_ATTN_V"); // 1: the per-warp kernel of round 1; default: the tiled kernel
+            attn_v = e ? atoi(e) : 2;
+        }
         const dim3 ag((T + 7) / 8, c->KVHl, kv_mul > 4 ? kv_mul / 4 : 1);
+        if (attn_v != 1) {
+            k_attn_prefill_t<<<(unsigned) (((T + kTQ - 1) / kTQ) * c->Hl), 128, kTSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl,
+                                                                                           kv_mul, c->S, pos0, T, c->num_sms);
+        } else
         switch (kv_mul) {
             case 1: k_attn_prefill<1><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
             case 2: k_attn_prefill<2><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
@@ -263,17 +456,16 @@ static int prefill_chunk(QwenCudaCtx* c, PrefillBufs* pb, const int* tokens_host
             case 8: k_attn_prefill<8><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
             default: qw_set_error("prefill: unsupported GQA ratio %d", kv_mul); return -2;
         }
-        k_prep_quant<<<T, 256, 0, st>>>(pb->att, nullptr, pb->q8, pb->xsT, Pl, Tpad, 0);
-        if (gemm(c->w_o + l * c->w_o_stride, pb->xb, D, Pl)) return -1;
-        if (qw_tp_allreduce(c, pb->xb, TD)) return -1; // wo is row-parallel under tensor parallelism
-        k_add_rows<<<(unsigned) ((TD + 255) / 256), 256, 0, st>>>(pb->x, pb->xb, TD);
-        // feed-forward block (forward.c:303-338)
-        k_prep_quant<<<T, 256, 0, st>>>(pb->x, c->ffn_norm + (size_t) l * D, pb->q8, pb->xsT, D, Tpad, 0);
+        k_prep_quant<<<T, 256, 0, st>>>(pb->att, nullptr, nullptr, pb->q8, pb->xsT, Pl, Tpad, 0);
+        if (gemm(c->w_o + l * c->w_o_stride, pb->xa, D, Pl)) return -1;
+        if (qw_tp_allreduce(c, pb->xa, TD)) return -1; // wo is row-parallel under tensor parallelism
+        // feed-forward block (forward.c:303-338); x += wo output inside the norm + quantise pass
+        k_prep_quant<<<T, 256, 0, st>>>(pb->x, pb->xa, c->ffn_norm + (size_t) l * D, pb->q8, pb->xsT, D, Tpad, 0);
         if (gemm(c->w_13 + l * c->w_13_stride, pb->h13, 2 * Hdl, D)) return -1;
-        k_prep_quant<<<T, 256, 0, st>>>(pb->h13, nullptr, pb->q8, pb->xsT, Hdl, Tpad, 1);
+        k_prep_quant<<<T, 256, 0, st>>>(pb->h13, nullptr, nullptr, pb->q8, pb->xsT, Hdl, Tpad, 1);
         if (gemm(c->w_2 + l * c->w_2_stride, pb->xb, D, Hdl)) return -1;
         if (qw_tp_allreduce(c, pb->xb, TD)) return -1;
-        k_add_rows<<<(unsigned) ((TD + 255) / 256), 256, 0, st>>>(pb->x, pb->xb, TD);
+        if (l == c->L - 1) k_add_rows<<<(unsigned) ((TD + 255) / 256), 256, 0, st>>>(pb->x, pb->xb, TD); // the last one has no norm after it here
     }
     QW_CUDA(cudaGetLastError());
     return 0;
@@ -324,4 +516,63 @@ int qw_prefill(QwenCudaCtx* c, const int* tokens_host, int n, int pos0) {
         return -3;
     }
     return 0;
+}
+
+// Test hook: the chunk attention kernels on host data. q [T][Hl][128]; k, v [pos][KVHl * 128] (the reference's cache layout,
+// positions 0 .. pos0 + T - 1); out [T][Hl][128]. variant 1 = per-warp kernel, 2 = tiled kernel. Token t sits at pos0 + t.
+extern "C" int qwen_cuda_debug_attn_prefill(float* out, const float* q, const float* k, const float* v, int Hl, int KVHl, int pos0,
+                                            int T, int variant) {
+    if (qwen_cuda_device_count() <= 0) {
+        qw_set_error("no CUDA device: this library has no CPU path");
+        return -1;
+    }
+    const int kv_mul = KVHl > 0 ? Hl / KVHl : 0, S = pos0 + T;
+    if (T <= 0 || pos0 < 0 || KVHl <= 0 || Hl % KVHl || (variant == 1 && kv_mul != 1 && kv_mul != 2 && kv_mul != 4 && kv_mul != 8)) {
+        qw_set_error("debug_attn_prefill: bad shape");
+        return -2;
+    }
+    float *dq = nullptr, *dk = nullptr, *dv = nullptr, *dout = nullptr;
+    const size_t nq = (size_t) T * Hl * 128, nkv = (size_t) KVHl * S * 128;
+    // device layout [kv head][pos][128]
+    float* hk = (float*) malloc(nkv * 4);
+    float* hv = (float*) malloc(nkv * 4);
+    int rc = -1;
+    do {
+        if (!hk || !hv) break;
+        for (int p = 0; p < S; ++p)
+            for (int h = 0; h < KVHl; ++h) {
+                memcpy(hk + ((size_t) h * S + p) * 128, k + ((size_t) p * KVHl + h) * 128, 512);
+                memcpy(hv + ((size_t) h * S + p) * 128, v + ((size_t) p * KVHl + h) * 128, 512);
+            }
+        if (cudaMalloc(&dq, nq * 4) || cudaMalloc(&dout, nq * 4) || cudaMalloc(&dk, nkv * 4) || cudaMalloc(&dv, nkv * 4)) break;
+        cudaMemcpy(dq, q, nq * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dk, hk, nkv * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dv, hv, nkv * 4, cudaMemcpyHostToDevice);
+        cudaMemset(dout, 0xff, nq * 4);
+        if (variant == 1) {
+            const dim3 ag((T + 7) / 8, KVHl, kv_mul > 4 ? kv_mul / 4 : 1);
+            cudaFuncSetAttribute(k_attn_prefill<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+            cudaFuncSetAttribute(k_attn_prefill<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+            cudaFuncSetAttribute(k_attn_prefill<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+            cudaFuncSetAttribute(k_attn_prefill<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+            switch (kv_mul) {
+                case 1: k_attn_prefill<1><<<ag, 256, kAttnSmem>>>(dq, dk, dv, dout, Hl, S, pos0, T); break;
+                case 2: k_attn_prefill<2><<<ag, 256, kAttnSmem>>>(dq, dk, dv, dout, Hl, S, pos0, T); break;
+                case 4: k_attn_prefill<4><<<ag, 256, kAttnSmem>>>(dq, dk, dv, dout, Hl, S, pos0, T); break;
+                default: k_attn_prefill<8><<<ag, 256, kAttnSmem>>>(dq, dk, dv, dout, Hl, S, pos0, T); break;
+            }
+        } else {
+            cudaFuncSetAttribute(k_attn_prefill_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem);
+            k_attn_prefill_t<<<(unsigned) (((T + kTQ - 1) / kTQ) * Hl), 128, kTSmem>>>(dq, dk, dv, dout, Hl, kv_mul, S, pos0, T, 148);
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            qw_set_error("debug_attn_prefill: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaMemcpy(out, dout, nq * 4, cudaMemcpyDeviceToHost);
+        rc = 0;
+    } while (0);
+    free(hk); free(hv);
+    cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout);
+    return rc;
 }
