@@ -325,9 +325,11 @@ k_prefill_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 //   * TOKENS are the UMMA M dimension (128 TMEM lanes = 128 tokens, one token per epilogue thread) and WEIGHT ROWS the N
 //     dimension, because N may be any multiple of 16 up to 256: the host picks N so that the tile count fills whole rounds
 //     of 148 SMs (4B, T = 512: w1/w3 N = 176 -> 444 tiles = 3 x 148; qkv N = 176 -> 140 tiles; wo / w2 N = 80 -> 128).
-//   * the activation scale of a token is a per-thread scalar (prefetched from the transposed scale matrix); the weight
-//     scales of the tile's rows arrive by TMA as a [N rows][4 groups] box once per 4 groups and every epilogue warp
-//     transposes its own columns into a private [4][64] table -> one broadcast LDS.128 per 4 outputs.
+//   * scales: the weight scales of the tile's rows arrive by TMA as a [N rows][4 groups] box once per 4 groups; a SCALE WARP
+//     (warp 18) transposes the box into a [4 groups][N] table and puts the 128 tokens' activation scales of the same four
+//     groups next to it (two table slots) -- the epilogue warps pay one barrier wait per four groups, one LDS per group for
+//     the token's scale and one broadcast LDS.128 per 4 outputs for the weight scales. (First version: every epilogue warp
+//     transposed its own columns and prefetched its own activation scales: ~760 cycles per four groups on all 16 warps.)
 //   * a shared-memory stage is released by the MMA's commit alone and an accumulator buffer by one arrival per warp:
 //     1 + 16 barrier arrivals per group instead of 34.
 // Arithmetic per output and group as above: ((float) dot * ws) * xs, added left to right in group order (bit-identical
@@ -340,8 +342,10 @@ constexpr int kPStageBytes = kPABytes + kPMaxN * 64; // 20 KB, keeps stages 1024
 constexpr int kPScSlots = 3;
 constexpr int kPScBytes = kPMaxN * 16;         // [N rows][4 scales]
 constexpr int kPEpiWarps = 16;
-constexpr int kPThreads = 32 * (2 + kPEpiWarps);
-constexpr int kPSmem = kPStages * kPStageBytes + kPScSlots * kPScBytes + kPEpiWarps * 4 * 64 * 4 + 1024;
+constexpr int kPThreads = 32 * (3 + kPEpiWarps); // producer, MMA issuer, 16 epilogue warps, scale warp
+constexpr int kPTblSlots = 2;
+constexpr int kPTblBytes = 4 * kPMaxN * 4 + 4 * kPM * 4; // [4 groups][N weight scales] + [4 groups][128 activation scales]
+constexpr int kPSmem = kPStages * kPStageBytes + kPScSlots * kPScBytes + kPTblSlots * kPTblBytes + 1024;
 
 struct GemmPParams {
     const float* xsT;      // [groups][Tpad]
@@ -384,14 +388,15 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sc_ring = smem + (size_t) kPStages * kPStageBytes;
-    float* wst_all = reinterpret_cast<float*>(sc_ring + kPScSlots * kPScBytes);
-    __shared__ __align__(8) uint64_t bars[2 * kPStages + 2 * kPScSlots + 2 * 4];
+    uint8_t* tbl_ring = sc_ring + kPScSlots * kPScBytes;
+    __shared__ __align__(8) uint64_t bars[2 * kPStages + 2 * kPScSlots + 2 * 4 + 2 * kPTblSlots];
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = p.n / 64;
     const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kPStages]);
     const uint32_t scfull0 = s_u32(&bars[2 * kPStages]), scempty0 = s_u32(&bars[2 * kPStages + kPScSlots]);
     const uint32_t tfull0 = s_u32(&bars[2 * kPStages + 2 * kPScSlots]), tempty0 = tfull0 + 8 * 4;
+    const uint32_t wtfull0 = tempty0 + 8 * 4, wtempty0 = wtfull0 + 8 * kPTblSlots;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kPStages; ++s) {
@@ -400,7 +405,11 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         for (int s = 0; s < kPScSlots; ++s) {
             mb_init(scfull0 + 8 * s, 1);
-            mb_init(scempty0 + 8 * s, kPEpiWarps);
+            mb_init(scempty0 + 8 * s, 1); // the scale warp has transposed the box
+        }
+        for (int s = 0; s < kPTblSlots; ++s) {
+            mb_init(wtfull0 + 8 * s, 1);
+            mb_init(wtempty0 + 8 * s, kPEpiWarps);
         }
         for (int b = 0; b < 4; ++b) {
             mb_init(tfull0 + 8 * b, 1);
@@ -472,70 +481,69 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 }
             }
         }
+    } else if (warp == 2 + kPEpiWarps) {
+        // ------------------------------------------------------------ scale warp: one table per four groups
+        uint32_t k = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.tiles && ok; tile += gridDim.x) {
+            const float* xcol = p.xsT + (tile % p.tok_tiles) * kPM + 4 * lane; // this lane's 4 tokens (xsT rows are padded to Tpad)
+            for (int g = 0; g < groups; g += 4, ++k) {
+                float4 x4[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    x4[kk] = g + kk < groups ? __ldg(reinterpret_cast<const float4*>(xcol + (size_t) (g + kk) * p.Tpad)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t sl = k % kPScSlots, ts = k % kPTblSlots;
+                if (!(ok = mb_wait(scfull0 + 8 * sl, (k / kPScSlots) & 1, p.err, 6))) break;           // the box has landed
+                if (!(ok = mb_wait(wtempty0 + 8 * ts, ((k / kPTblSlots) & 1) ^ 1, p.err, 7))) break;   // the table slot has been read
+                const float4* box = reinterpret_cast<const float4*>(sc_ring + sl * kPScBytes);
+                float* tw = reinterpret_cast<float*>(tbl_ring + ts * kPTblBytes);
+                float* tx = tw + 4 * kPMaxN;
+#pragma unroll
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    const int c = c0 + lane;
+                    if (N % 32 == 0 || c < N) {
+                        const float4 s4 = box[c];
+                        tw[c] = s4.x; tw[kPMaxN + c] = s4.y; tw[2 * kPMaxN + c] = s4.z; tw[3 * kPMaxN + c] = s4.w;
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<float4*>(tx + kk * kPM + 4 * lane) = x4[kk];
+                __syncwarp();
+                if (lane == 0) {
+                    mb_arrive(wtfull0 + 8 * ts);
+                    mb_arrive(scempty0 + 8 * sl);
+                }
+            }
+        }
     } else {
         // ------------------------------------------------------------ epilogue: one token per thread, CW columns per warp
         const int ew = warp - 2;
         const int q = warp & 3, j = ew >> 2;             // TMEM lane quarter (hardware rule: CTA warp id % 4), column block
         const int cbeg = j * CW;                         // this warp's columns of the tile
-        float* wst = wst_all + ew * 256;                 // [4 groups][64 columns]: the warp's weight scales, transposed
         uint32_t it = 0, sc_it = 0;
         bool ok = true;
-        float xc[4] = {0.f, 0.f, 0.f, 0.f}, xn[4] = {0.f, 0.f, 0.f, 0.f};
-        auto load_xs = [&](const float* col, bool live, int g0, float (&dst)[4]) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = (live && g0 + k < groups) ? __ldg(col + (size_t) (g0 + k) * p.Tpad) : 0.0f;
-        };
         for (int tile = blockIdx.x; tile < p.tiles && ok; tile += gridDim.x) {
             const int row0 = (tile / p.tok_tiles) * N, t0 = (tile % p.tok_tiles) * kPM;
             const int t = t0 + q * 32 + lane;
             const bool t_ok = t < p.T;
-            const float* xsp = p.xsT + (t_ok ? t : 0);
             float acc[CW];
 #pragma unroll
             for (int c = 0; c < CW; ++c) acc[c] = 0.0f;
-            if (tile == (int) blockIdx.x) load_xs(xsp, t_ok, 0, xn);
             for (int g = 0; g < groups; ++g, ++it) {
                 const int gk = g & 3;
                 long long* pr = (p.prof && blockIdx.x == 0 && it < 64 && warp == 2 && lane == 0) ? p.prof + (128 + it) * 8 : nullptr;
                 if (pr) pr[0] = clock64();
-                if (gk == 0) {
-                    // the token's activation scales of groups g .. g + 3 were requested four groups ago (the first touch of a
-                    // scale row is an HBM miss); now ask for the next four -- of this tile or of the CTA's next tile
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) xc[k] = xn[k];
-                    if (g + 4 < groups) {
-                        load_xs(xsp, t_ok, g + 4, xn);
-                    } else if (tile + (int) gridDim.x < p.tiles) {
-                        const int tn = ((tile + (int) gridDim.x) % p.tok_tiles) * kPM + q * 32 + lane;
-                        load_xs(p.xsT + (tn < p.T ? tn : 0), tn < p.T, 0, xn);
-                    }
-                    // new weight-scale box: keep this warp's columns, transposed, and hand the slot back
-                    const uint32_t sl = sc_it % kPScSlots;
-                    if (pr) pr[5] = clock64();
-                    if (!(ok = mb_wait(scfull0 + 8 * sl, (sc_it / kPScSlots) & 1, p.err, 6))) break;
-                    if (pr) pr[6] = clock64();
-                    const float* box = reinterpret_cast<const float*>(sc_ring + sl * kPScBytes) + cbeg * 4;
-                    __syncwarp(); // everybody is done with the previous table
-#pragma unroll
-                    for (int c0 = 0; c0 < CW; c0 += 32) {
-                        const int c = c0 + lane;
-                        if (CW % 32 == 0 || c < CW) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(box + c * 4);
-                            wst[c] = s4.x; wst[64 + c] = s4.y; wst[128 + c] = s4.z; wst[192 + c] = s4.w;
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mb_arrive(scempty0 + 8 * sl);
-                    ++sc_it;
-                }
-                const float xsc = gk == 0 ? xc[0] : gk == 1 ? xc[1] : gk == 2 ? xc[2] : xc[3];
+                const uint32_t ts = sc_it % kPTblSlots;
+                if (gk == 0 && !(ok = mb_wait(wtfull0 + 8 * ts, (sc_it / kPTblSlots) & 1, p.err, 8))) break; // the scale table of groups g .. g + 3
+                const float* tw = reinterpret_cast<const float*>(tbl_ring + ts * kPTblBytes);
+                const float xsc = tw[4 * kPMaxN + gk * kPM + q * 32 + lane]; // this token's activation scale
+                const float* wg = tw + gk * kPMaxN + cbeg;                   // the weight scales of this warp's columns
                 const uint32_t b = it % NBUF;
                 if (pr) pr[1] = clock64();
                 if (!(ok = mb_wait(tfull0 + 8 * b, (it / NBUF) & 1, p.err, 4))) break;
                 if (pr) pr[2] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + b * (uint32_t) N + cbeg;
-                const float* wg = wst + gk * 64;
                 const unsigned long long xs2 = pack2(xsc, xsc);
                 // TMEM -> registers two loads (2 U columns) at a time, software-pipelined: the loads of chunk k + 1 are in flight
                 // while chunk k is promoted; the buffer goes back to the MMA issuer as soon as the last load has landed
@@ -580,6 +588,11 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                             }
                         }
                     }
+                }
+                if (gk == 3 || g == groups - 1) { // done with this table
+                    __syncwarp();
+                    if (lane == 0) mb_arrive(wtempty0 + 8 * ts);
+                    ++sc_it;
                 }
                 if (pr) pr[7] = clock64();
             }
@@ -758,17 +771,22 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
         }
         static long long* prof = nullptr;
         static int want_prof = -1;
-        if (want_prof < 0) want_prof = getenv("QWEN_GEMM_PROF") ? 1 : 0;
-        if (want_prof == 1 && !prof) {
+        static int prof_skip = 0; // QWEN_GEMM_PROF=k: dump the stamps of the k-th launch of the process
+        if (want_prof < 0) {
+            want_prof = getenv("QWEN_GEMM_PROF") ? 1 : 0;
+            prof_skip = want_prof ? std::max(0, atoi(getenv("QWEN_GEMM_PROF")) - 1) : 0;
+        }
+        const bool prof_now = want_prof == 1 && prof_skip-- <= 0;
+        if (prof_now && !prof) {
             cudaMalloc((void**) &prof, 3 * 64 * 8 * 8);
             cudaMemset(prof, 0, 3 * 64 * 8 * 8);
         }
-        GemmPParams pp{xsT, out, dots, d, n, T, Tpad, tok_tiles, ((d + N - 1) / N) * tok_tiles, err_dev, want_prof == 1 ? prof : nullptr};
+        GemmPParams pp{xsT, out, dots, d, n, T, Tpad, tok_tiles, ((d + N - 1) / N) * tok_tiles, err_dev, prof_now ? prof : nullptr};
         const int grid = std::min(sms, pp.tiles);
         if (ms_out) QW_CUDA(cudaEventRecord(e0, st));
         kern<<<grid, kPThreads, kPSmem, st>>>(mx, mw, ms, pp);
         QW_CUDA(cudaGetLastError());
-        if (want_prof == 1) { // one dump per process: the first launch
+        if (prof_now) { // one dump per process
             want_prof = 2;
             cudaStreamSynchronize(st);
             static long long h[3 * 64 * 8];
@@ -777,7 +795,7 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
             fprintf(stderr, "[gemm prof] d=%d n=%d T=%d N=%d tiles=%d (cycles since the MMA issuer's first stamp)\n", d, n, T, N, pp.tiles);
             for (int i = 0; i < 20; ++i) {
                 const long long *m = h + i * 8, *pd = h + (64 + i) * 8, *ep = h + (128 + i) * 8;
-                fprintf(stderr, "[gemm prof] g%02d mma top %6lld tempty %6lld full %6lld commit %6lld | prod top %6lld empty %6lld | epi top %6lld scales %6lld tfull %6lld ld0 %6lld ld1 %6lld | xs-done %6lld scfull %6lld | done %6lld\n",
+                fprintf(stderr, "[gemm prof] g%02d mma top %6lld tempty %6lld full %6lld commit %6lld | prod top %6lld empty %6lld | epi top %6lld table %6lld tfull %6lld ld0 %6lld ld1 %6lld | - %6lld - %6lld | done %6lld\n",
                         i, m[0] - z, m[1] - z, m[2] - z, m[3] - z, pd[0] - z, pd[1] - z, ep[0] - z, ep[1] - z, ep[2] - z, ep[3] - z,
                         ep[4] ? ep[4] - z : 0, ep[5] ? ep[5] - z : 0, ep[6] ? ep[6] - z : 0, ep[7] - z);
             }
