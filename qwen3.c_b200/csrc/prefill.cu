@@ -30,6 +30,8 @@ constexpr int kChunkTokens = 512;
 struct PrefillBufs {
     int cap = 0;          // tokens the buffers hold
     int* tokens = nullptr;
+    float* apart = nullptr; // partial attention rows [parts][cap][Hl][132] (k_attn_prefill_t), grown on demand
+    size_t apart_floats = 0;
     float *x = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr, *q = nullptr, *att = nullptr, *h13 = nullptr;
     int8_t* q8 = nullptr; // [cap][maxn] activation codes of the GEMM at hand (row pitch = its n)
     float* xsT = nullptr; // [maxn / 64][cap] activation scales, transposed for the GEMM epilogue
@@ -61,6 +63,9 @@ k_prep_quant(float* __restrict__ src, const float* __restrict__ add, const float
     float* s = src + (size_t) t * (swiglu ? 2 * n : n);
     float r = 1.0f;
     if (w) {
+        // sum of squares: element i goes to thread i % 256, as in round 1 -- the order fixes the last bits of the scale, and with
+        // them which values sit on a rounding boundary of the quantiser (a four-per-thread order was measured: same speed
+        // class, but it moved 436 of 307 200 layer-0 K/V values of the 600-token parity case past 1e-4)
         float ss = 0.0f;
         if (add) {
             const float* a = add + (size_t) t * n;
@@ -69,8 +74,9 @@ k_prep_quant(float* __restrict__ src, const float* __restrict__ add, const float
                 s[i] = v; // re-read by other threads after the barrier below
                 ss = __fmaf_rn(v, v, ss);
             }
-        } else
-        for (int i = tid; i < n; i += 256) ss = __fmaf_rn(s[i], s[i], ss);
+        } else {
+            for (int i = tid; i < n; i += 256) ss = __fmaf_rn(s[i], s[i], ss);
+        }
         ss = warp_sum(ss);
         if (lane == 0) red[warp] = ss;
         __syncthreads();
@@ -79,23 +85,44 @@ k_prep_quant(float* __restrict__ src, const float* __restrict__ add, const float
         for (int i = 0; i < 8; ++i) tot = __fadd_rn(tot, red[i]);
         r = rms_rscale(tot, n);
     }
-    for (int g = warp; g < n / 64; g += 8) {
-        float a, b;
-        const int i0 = g * 64 + lane, i1 = i0 + 32;
-        if (swiglu) {
-            a = __fmul_rn(silu_ref(s[2 * i0]), s[2 * i0 + 1]);
-            b = __fmul_rn(silu_ref(s[2 * i1]), s[2 * i1 + 1]);
-        } else if (w) {
-            a = __fmul_rn(w[i0], __fmul_rn(r, s[i0]));
-            b = __fmul_rn(w[i1], __fmul_rn(r, s[i1]));
-        } else {
-            a = s[i0];
-            b = s[i1];
+    // quantiser: a half-warp per group of 64 (four consecutive values per lane: 16-byte loads, 4-byte code stores), warp w
+    // takes the group pairs w, w + 8, ...; per value the reference's arithmetic (q8.c:5-30)
+    const int groups = n / 64;
+    for (int g2 = warp; 2 * g2 < groups; g2 += 8) {
+        const int g = 2 * g2 + (lane >> 4);
+        const bool live = g < groups;
+        const int i0 = g * 64 + (lane & 15) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            if (swiglu) {
+                const float4 p0 = *reinterpret_cast<const float4*>(s + 2 * i0), p1 = *reinterpret_cast<const float4*>(s + 2 * i0 + 4);
+                v[0] = __fmul_rn(silu_ref(p0.x), p0.y);
+                v[1] = __fmul_rn(silu_ref(p0.z), p0.w);
+                v[2] = __fmul_rn(silu_ref(p1.x), p1.y);
+                v[3] = __fmul_rn(silu_ref(p1.z), p1.w);
+            } else {
+                const float4 x4 = *reinterpret_cast<const float4*>(s + i0);
+                if (w) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w + i0);
+                    v[0] = __fmul_rn(w4.x, __fmul_rn(r, x4.x));
+                    v[1] = __fmul_rn(w4.y, __fmul_rn(r, x4.y));
+                    v[2] = __fmul_rn(w4.z, __fmul_rn(r, x4.z));
+                    v[3] = __fmul_rn(w4.w, __fmul_rn(r, x4.w));
+                } else {
+                    v[0] = x4.x; v[1] = x4.y; v[2] = x4.z; v[3] = x4.w;
+                }
+            }
         }
-        const float scale = q8_scale(warp_max(fmaxf(fabsf(a), fabsf(b))));
-        q8[(size_t) t * n + i0] = (int8_t) q8_code(a, scale);
-        q8[(size_t) t * n + i1] = (int8_t) q8_code(b, scale);
-        if (lane == 0) xsT[(size_t) g * Tpad + t] = scale;
+        float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o)); // within the half-warp
+        const float scale = q8_scale(amax);
+        if (live) {
+            const int c0 = q8_code(v[0], scale), c1 = q8_code(v[1], scale), c2 = q8_code(v[2], scale), c3 = q8_code(v[3], scale);
+            *reinterpret_cast<uint32_t*>(q8 + (size_t) t * n + i0) =
+                (uint32_t) (c0 & 0xff) | ((uint32_t) (c1 & 0xff) << 8) | ((uint32_t) (c2 & 0xff) << 16) | ((uint32_t) (c3 & 0xff) << 24);
+            if ((lane & 15) == 0) xsT[(size_t) g * Tpad + t] = scale;
+        }
     }
 }
 
@@ -213,26 +240,62 @@ k_attn_prefill(const float* __restrict__ q, const float* __restrict__ k_layer, c
 //               and 64 + 4 tx .. : per 4 keys 8 broadcast P loads + 8 V loads feed 256 FMAs.
 // fp32 throughout (the cache is fp32, as the reference's). The heaviest query tiles (latest positions) are launched first.
 constexpr int kTQ = 64, kTK = 64, kTKPitch = 132, kTPPitch = 68;
+constexpr int kTPartStride = 132; // floats per partial row: 128 outputs, running maximum, running sum, 2 pad
+
+// The key axis is cut into FIXED blocks of absolute positions -- 128 positions each up to 512, 512 positions beyond -- and a
+// (query tile, head) item whose visible keys span more than one block is computed as one CTA per block ("part"), each
+// leaving an un-normalised partial (O, m, l) per row, merged by k_attn_merge in block order. Why: a query tile's work grows
+// with its position (1 .. 8 key tiles at T = 512), so whole items balance badly over 148 SMs when heads are few (1.7B
+// shape: 128 items, the busiest SM had 8 tile-units of an average 3.9); parts are at most 2 units. The blocks depend on
+// absolute positions only, so a row's result does not depend on how a prompt was cut into calls
+// (test_prefill_in_two_calls_equals_one_call); a row whose keys all lie in block 0 merges to O_0 * 1 / (l_0 * 1): exactly
+// what the single-part path gives.
+__host__ __device__ inline int attn_parts(int nkt) { return nkt <= 8 ? (nkt + 1) / 2 : 4 + (nkt - 8 + 7) / 8; }
+__host__ __device__ inline void attn_part_range(int p, int& k0, int& k1) {
+    if (p < 4) {
+        k0 = 2 * p;
+        k1 = k0 + 2;
+    } else {
+        k0 = 8 + 8 * (p - 4);
+        k1 = k0 + 8;
+    }
+}
+struct AttnPlan {
+    int nq;             // query tiles of the chunk
+    int first[9];       // first[i]: first block index (in units of heads) of query tile nq - 1 - i; first[nq] = total
+    int parts[8];       // parts[i]: parts of query tile nq - 1 - i
+};
+inline AttnPlan attn_plan(int pos0, int T) {
+    AttnPlan pl{};
+    pl.nq = (T + kTQ - 1) / kTQ;
+    int acc = 0;
+    for (int i = 0; i < pl.nq; ++i) {
+        const int qt = pl.nq - 1 - i;
+        const int last_pos = pos0 + std::min(T, (qt + 1) * kTQ) - 1;
+        pl.parts[i] = attn_parts(last_pos / kTK + 1);
+        pl.first[i] = acc;
+        acc += pl.parts[i];
+    }
+    pl.first[pl.nq] = acc;
+    return pl;
+}
 constexpr int kTSmem = (kTQ * 128 + kTK * kTKPitch + kTK * 128) * 4; // Q | K (later P) | V = 99 328 B: two CTAs per SM
 
 __global__ void __launch_bounds__(128, 2)
 k_attn_prefill_t(const float* __restrict__ q, const float* __restrict__ k_layer, const float* __restrict__ v_layer,
-                 float* __restrict__ out, int Hl, int kv_mul, int S, int pos0, int T, int sms) {
+                 float* __restrict__ out, float* __restrict__ partial, int Hl, int kv_mul, int S, int pos0, int T,
+                 const AttnPlan plan) {
     extern __shared__ __align__(16) float tsm[];
     float* sQ = tsm;
     float* sK = tsm + kTQ * 128;
     float* sP = sK; // the probabilities overwrite the K tile once every thread has its scores
     float* sV = sK + kTK * kTKPitch;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    // Work of a CTA grows with its query tile's position. CTAs b and b + #SMs share an SM when the whole grid is resident
-    // (2 per SM), so the first #SMs CTAs take the heaviest items in descending order and the rest the lightest in ascending
-    // order: heavy + light per SM (4B shape, T = 512: 9 tile-units on the busiest SM instead of 12, 7.8 would be perfect).
-    // Larger grids are simply heaviest-first (the hardware scheduler then balances).
-    const int nq = (T + kTQ - 1) / kTQ;
-    const int n_items = nq * Hl;
-    int rank = (int) blockIdx.x;
-    if (n_items <= 2 * sms && rank >= sms) rank = n_items - 1 - (rank - sms);
-    const int qt = nq - 1 - rank / Hl, h = rank % Hl, kvh = h / kv_mul;
+    // block -> (query tile, part, head): latest query tiles first, heads fastest
+    const int unit = (int) blockIdx.x / Hl, h = (int) blockIdx.x % Hl, kvh = h / kv_mul;
+    int qi = 0;
+    while (qi + 1 < plan.nq && unit >= plan.first[qi + 1]) ++qi;
+    const int qt = plan.nq - 1 - qi, part = unit - plan.first[qi], nparts = plan.parts[qi];
     const int t0 = qt * kTQ;
     const int rows = min(kTQ, T - t0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -253,21 +316,26 @@ k_attn_prefill_t(const float* __restrict__ q, const float* __restrict__ k_layer,
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[i][e] = 0.0f;
     }
-    for (int p0 = 0; p0 <= last_pos; p0 += kTK) {
+    int kt0 = 0, kt1 = 0;
+    attn_part_range(part, kt0, kt1);
+    const int p_end = min(last_pos, kt1 * kTK - 1); // this part's last key position
+    for (int p0 = kt0 * kTK; p0 <= p_end; p0 += kTK) {
         const int nk = min(kTK, last_pos + 1 - p0);
         __syncthreads(); // the previous tile's P and V have been consumed (first pass: Q is in place)
+        // the K tile and the V tile travel as two cp.async groups: the scores wait for K only, V lands behind them
         for (int i = tid; i < kTK * 32; i += 128) {
             const int r = i >> 5, c = (i & 31) * 4;
-            if (r < nk) {
-                cp_async16(sK + r * kTKPitch + c, K + (size_t) (p0 + r) * 128 + c);
-                cp_async16(sV + r * 128 + c, V + (size_t) (p0 + r) * 128 + c);
-            } else { // rows nobody may see: zeros, not whatever the cache holds (0 * NaN would poison P V)
-                *reinterpret_cast<float4*>(sK + r * kTKPitch + c) = zero4;
-                *reinterpret_cast<float4*>(sV + r * 128 + c) = zero4;
-            }
+            if (r < nk) cp_async16(sK + r * kTKPitch + c, K + (size_t) (p0 + r) * 128 + c);
+            else *reinterpret_cast<float4*>(sK + r * kTKPitch + c) = zero4; // rows nobody may see: zeros, not whatever the cache holds
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int i = tid; i < kTK * 32; i += 128) {
+            const int r = i >> 5, c = (i & 31) * 4;
+            if (r < nk) cp_async16(sV + r * 128 + c, V + (size_t) (p0 + r) * 128 + c);
+            else *reinterpret_cast<float4*>(sV + r * 128 + c) = zero4;       // (0 * NaN would poison P V)
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         // ---- S = Q K^T
         float s[8][4];
@@ -327,6 +395,7 @@ k_attn_prefill_t(const float* __restrict__ q, const float* __restrict__ k_layer,
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) sP[(ty * 8 + i) * kTPPitch + tx + 16 * j] = s[i][j];
+        asm volatile("cp.async.wait_group 0;" ::: "memory"); // this thread's part of the V tile
         __syncthreads();
         // ---- O += P V
         const int nk4 = (nk + 3) & ~3;
@@ -360,13 +429,67 @@ k_attn_prefill_t(const float* __restrict__ q, const float* __restrict__ k_layer,
     for (int i = 0; i < 8; ++i) {
         const int r = ty * 8 + i;
         if (r < rows) {
-            float* dst = out + ((size_t) (t0 + r) * Hl + h) * 128;
-            *reinterpret_cast<float4*>(dst + tx * 4) =
-                make_float4(__fdiv_rn(o[i][0], l[i]), __fdiv_rn(o[i][1], l[i]), __fdiv_rn(o[i][2], l[i]), __fdiv_rn(o[i][3], l[i]));
-            *reinterpret_cast<float4*>(dst + 64 + tx * 4) =
-                make_float4(__fdiv_rn(o[i][4], l[i]), __fdiv_rn(o[i][5], l[i]), __fdiv_rn(o[i][6], l[i]), __fdiv_rn(o[i][7], l[i]));
+            if (nparts == 1) {
+                float* dst = out + ((size_t) (t0 + r) * Hl + h) * 128;
+                *reinterpret_cast<float4*>(dst + tx * 4) =
+                    make_float4(__fdiv_rn(o[i][0], l[i]), __fdiv_rn(o[i][1], l[i]), __fdiv_rn(o[i][2], l[i]), __fdiv_rn(o[i][3], l[i]));
+                *reinterpret_cast<float4*>(dst + 64 + tx * 4) =
+                    make_float4(__fdiv_rn(o[i][4], l[i]), __fdiv_rn(o[i][5], l[i]), __fdiv_rn(o[i][6], l[i]), __fdiv_rn(o[i][7], l[i]));
+            } else { // un-normalised partial of this block of keys: k_attn_merge finishes the row
+                float* dst = partial + (((size_t) part * T + t0 + r) * Hl + h) * kTPartStride;
+                *reinterpret_cast<float4*>(dst + tx * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+                *reinterpret_cast<float4*>(dst + 64 + tx * 4) = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+                if (tx == 0) {
+                    dst[128] = m[i];
+                    dst[129] = l[i];
+                }
+            }
         }
     }
+}
+
+// rows of query tiles that were computed in parts: softmax merge of the partials in block order (as the decode kernel's
+// combine does for its split-KV partials). grid (rows, Hl), 128 threads = output dims.
+__global__ void __launch_bounds__(128)
+k_attn_merge(const float* __restrict__ partial, float* __restrict__ out, int Hl, int pos0, int T, int t_first) {
+    const int t = t_first + (int) blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+    const int qt = t / kTQ;
+    const int last_pos = pos0 + min(T, (qt + 1) * kTQ) - 1;
+    const int np = attn_parts(last_pos / kTK + 1);
+    if (np == 1) return; // written directly
+    const size_t pstride = (size_t) T * Hl * kTPartStride;
+    const float* base = partial + ((size_t) t * Hl + h) * kTPartStride;
+    float A = 0.0f, L = 0.0f;
+    if (np <= 4) { // the usual case (contexts up to 512): every load issued before the first use -- one L2 round trip
+        float mp[4], lp[4], op[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const bool live = p < np;
+            mp[p] = live ? base[p * pstride + 128] : -INFINITY;
+            lp[p] = live ? base[p * pstride + 129] : 0.0f;
+            op[p] = live ? base[p * pstride + d] : 0.0f;
+        }
+        const float M = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (mp[p] == -INFINITY) continue; // a block this row sees nothing of
+            const float w = expf(__fsub_rn(mp[p], M));
+            L = __fmaf_rn(lp[p], w, L);
+            A = __fmaf_rn(op[p], w, A);
+        }
+    } else {
+        float M = -INFINITY;
+        for (int p = 0; p < np; ++p) M = fmaxf(M, base[p * pstride + 128]);
+        for (int p = 0; p < np; ++p) {
+            const float* src = base + p * pstride;
+            const float mp = src[128];
+            if (mp == -INFINITY) continue;
+            const float w = expf(__fsub_rn(mp, M));
+            L = __fmaf_rn(src[129], w, L);
+            A = __fmaf_rn(src[d], w, A);
+        }
+    }
+    out[((size_t) t * Hl + h) * 128 + d] = __fdiv_rn(A, L);
 }
 
 // residual add over a chunk (forward.c:295-298, 335-338)
@@ -380,7 +503,7 @@ int ensure_bufs(QwenCudaCtx* c, PrefillBufs*& pb, int T) {
     if (pb->cap >= T) return 0;
     const int cap = (T + 127) / 128 * 128;
     const size_t maxn = (size_t) std::max(c->D, std::max(c->Pl, c->Hdl));
-    void* old[] = {pb->tokens, pb->x, pb->xa, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
+    void* old[] = {pb->apart, pb->tokens, pb->x, pb->xa, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
     for (void* o : old)
         if (o) cudaFree(o);
     *pb = PrefillBufs();
@@ -412,7 +535,7 @@ static PrefillBufs*& bufs_of(QwenCudaCtx* c) { return *reinterpret_cast<PrefillB
 void qw_prefill_free(QwenCudaCtx* c) {
     PrefillBufs* pb = bufs_of(c);
     if (!pb) return;
-    void* old[] = {pb->tokens, pb->x, pb->xa, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
+    void* old[] = {pb->apart, pb->tokens, pb->x, pb->xa, pb->xb, pb->qkv, pb->q, pb->att, pb->h13, pb->q8, pb->xsT, pb->err};
     for (void* o : old)
         if (o) cudaFree(o);
     delete pb;
@@ -446,8 +569,28 @@ static int prefill_chunk(QwenCudaCtx* c, PrefillBufs* pb, const int* tokens_host
         }
         const dim3 ag((T + 7) / 8, c->KVHl, kv_mul > 4 ? kv_mul / 4 : 1);
         if (attn_v != 1) {
-            k_attn_prefill_t<<<(unsigned) (((T + kTQ - 1) / kTQ) * c->Hl), 128, kTSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl,
-                                                                                           kv_mul, c->S, pos0, T, c->num_sms);
+            const AttnPlan plan = attn_plan(pos0, T);
+            const int maxparts = plan.parts[0];
+            if (maxparts > 1) {
+                const size_t need = (size_t) maxparts * T * c->Hl * kTPartStride;
+                if (need > pb->apart_floats) {
+                    QW_CUDA(cudaStreamSynchronize(st));
+                    if (pb->apart) cudaFree(pb->apart);
+                    pb->apart = nullptr;
+                    pb->apart_floats = 0;
+                    QW_CUDA(cudaMalloc((void**) &pb->apart, need * 4));
+                    pb->apart_floats = need;
+                }
+            }
+            k_attn_prefill_t<<<(unsigned) (plan.first[plan.nq] * c->Hl), 128, kTSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att,
+                                                                                          pb->apart, c->Hl, kv_mul, c->S, pos0, T, plan);
+            if (maxparts > 1) {
+                int i_split = 0; // query tiles are listed latest first: the last one with parts > 1 is the earliest split tile
+                for (int i = 0; i < plan.nq; ++i)
+                    if (plan.parts[i] > 1) i_split = i;
+                const int t_first = (plan.nq - 1 - i_split) * kTQ;
+                k_attn_merge<<<dim3((unsigned) (T - t_first), (unsigned) c->Hl), 128, 0, st>>>(pb->apart, pb->att, c->Hl, pos0, T, t_first);
+            }
         } else
         switch (kv_mul) {
             case 1: k_attn_prefill<1><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
@@ -563,7 +706,18 @@ extern "C" int qwen_cuda_debug_attn_prefill(float* out, const float* q, const fl
             }
         } else {
             cudaFuncSetAttribute(k_attn_prefill_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem);
-            k_attn_prefill_t<<<(unsigned) (((T + kTQ - 1) / kTQ) * Hl), 128, kTSmem>>>(dq, dk, dv, dout, Hl, kv_mul, S, pos0, T, 148);
+            // chunks of at most kChunkTokens tokens, as forward_prefill cuts them
+            for (int c0 = 0; c0 < T; c0 += kChunkTokens) {
+                const int Tc = std::min(kChunkTokens, T - c0);
+                const AttnPlan plan = attn_plan(pos0 + c0, Tc);
+                float* dpart = nullptr;
+                if (plan.parts[0] > 1 && cudaMalloc(&dpart, (size_t) plan.parts[0] * Tc * Hl * kTPartStride * 4)) break;
+                k_attn_prefill_t<<<(unsigned) (plan.first[plan.nq] * Hl), 128, kTSmem>>>(dq + (size_t) c0 * Hl * 128, dk, dv, dout + (size_t) c0 * Hl * 128,
+                                                                                        dpart, Hl, kv_mul, S, pos0 + c0, Tc, plan);
+                if (plan.parts[0] > 1) k_attn_merge<<<dim3((unsigned) Tc, (unsigned) Hl), 128>>>(dpart, dout + (size_t) c0 * Hl * 128, Hl, pos0 + c0, Tc, 0);
+                cudaDeviceSynchronize();
+                cudaFree(dpart);
+            }
         }
         if (cudaDeviceSynchronize() != cudaSuccess) {
             qw_set_error("debug_attn_prefill: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -155,6 +155,11 @@ __device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
     unsigned long long r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -377,7 +382,7 @@ __device__ __forceinline__ void tmem_ld_unit<8>(uint32_t taddr, int (&v)[8]) {
 // U = columns per tcgen05.ld (4 for N <= 128, 8 above), UC = loads per epilogue warp and group: N = 4 * UC * U weight rows per
 // tile, everything about the tile shape a compile-time constant (a first version with run-time unit counts spent more
 // issue slots on predicates and index arithmetic than on the promotion: 347 instructions per 48 outputs).
-template <int U, int UC, bool DOTS>
+template <int U, int UC, bool DOTS, bool EXACT>
 __global__ void __launch_bounds__(kPThreads, 1)
 k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_s, const GemmPParams p) {
@@ -397,6 +402,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t scfull0 = s_u32(&bars[2 * kPStages]), scempty0 = s_u32(&bars[2 * kPStages + kPScSlots]);
     const uint32_t tfull0 = s_u32(&bars[2 * kPStages + 2 * kPScSlots]), tempty0 = tfull0 + 8 * 4;
     const uint32_t wtfull0 = tempty0 + 8 * 4, wtempty0 = wtfull0 + 8 * kPTblSlots;
+    if (p.prof && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x] = (long long) g_ns();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kPStages; ++s) {
@@ -426,6 +432,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    if (p.prof && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 1] = (long long) g_ns();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -578,13 +585,22 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                             for (int e = 0; e < U; e += 4) {
                                 const int c = (2 * k + h) * U + e;
                                 const float4 w4 = *reinterpret_cast<const float4*>(wg + c);
-                                float lo, hi; // two packed multiplies, scalar adds (see the note at mul2)
-                                unpack2(mul2(mul2(pack2((float) vv[e], (float) vv[e + 1]), pack2(w4.x, w4.y)), xs2), lo, hi);
-                                acc[c] = __fadd_rn(acc[c], lo);
-                                acc[c + 1] = __fadd_rn(acc[c + 1], hi);
-                                unpack2(mul2(mul2(pack2((float) vv[e + 2], (float) vv[e + 3]), pack2(w4.z, w4.w)), xs2), lo, hi);
-                                acc[c + 2] = __fadd_rn(acc[c + 2], lo);
-                                acc[c + 3] = __fadd_rn(acc[c + 3], hi);
+                                float lo, hi;
+                                if (EXACT) { // two packed multiplies, scalar adds (see the note at mul2): the reference's three roundings
+                                    unpack2(mul2(mul2(pack2((float) vv[e], (float) vv[e + 1]), pack2(w4.x, w4.y)), xs2), lo, hi);
+                                    acc[c] = __fadd_rn(acc[c], lo);
+                                    acc[c + 1] = __fadd_rn(acc[c + 1], hi);
+                                    unpack2(mul2(mul2(pack2((float) vv[e + 2], (float) vv[e + 3]), pack2(w4.z, w4.w)), xs2), lo, hi);
+                                    acc[c + 2] = __fadd_rn(acc[c + 2], lo);
+                                    acc[c + 3] = __fadd_rn(acc[c + 3], hi);
+                                } else { // acc = fma((float) dot * ws, xs, acc): one rounding fewer per term, one FMA-pipe pass fewer per output
+                                    unpack2(fma2(mul2(pack2((float) vv[e], (float) vv[e + 1]), pack2(w4.x, w4.y)), xs2, pack2(acc[c], acc[c + 1])), lo, hi);
+                                    acc[c] = lo;
+                                    acc[c + 1] = hi;
+                                    unpack2(fma2(mul2(pack2((float) vv[e + 2], (float) vv[e + 3]), pack2(w4.z, w4.w)), xs2, pack2(acc[c + 2], acc[c + 3])), lo, hi);
+                                    acc[c + 2] = lo;
+                                    acc[c + 3] = hi;
+                                }
                             }
                         }
                     }
@@ -596,6 +612,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 }
                 if (pr) pr[7] = clock64();
             }
+            if (p.prof && warp == 2 && lane == 0 && tile == (int) blockIdx.x) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 2] = (long long) g_ns();
             if (ok && t_ok) { // the tile is done: the stores overlap the next tile's main loop
                 float* orow = p.out + (size_t) t * p.d + row0 + cbeg;
                 if (row0 + cbeg + CW <= p.d && (p.d & 3) == 0) {
@@ -611,24 +628,25 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (p.prof && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 3] = (long long) g_ns();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 typedef void (*GemmPKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmPParams);
 // weight rows per tile -> kernel: N = 16 .. 128 in steps of 16 (U = 4), 160 and 192 (U = 8)
-template <bool DOTS>
+template <bool DOTS, bool EXACT>
 GemmPKernel gemm_p_kernel(int N) {
     switch (N) {
-        case 16: return k_prefill_gemm_p<4, 1, DOTS>;
-        case 32: return k_prefill_gemm_p<4, 2, DOTS>;
-        case 48: return k_prefill_gemm_p<4, 3, DOTS>;
-        case 64: return k_prefill_gemm_p<4, 4, DOTS>;
-        case 80: return k_prefill_gemm_p<4, 5, DOTS>;
-        case 96: return k_prefill_gemm_p<4, 6, DOTS>;
-        case 112: return k_prefill_gemm_p<4, 7, DOTS>;
-        case 128: return k_prefill_gemm_p<4, 8, DOTS>;
-        case 160: return k_prefill_gemm_p<8, 5, DOTS>;
-        case 192: return k_prefill_gemm_p<8, 6, DOTS>;
+        case 16: return k_prefill_gemm_p<4, 1, DOTS, EXACT>;
+        case 32: return k_prefill_gemm_p<4, 2, DOTS, EXACT>;
+        case 48: return k_prefill_gemm_p<4, 3, DOTS, EXACT>;
+        case 64: return k_prefill_gemm_p<4, 4, DOTS, EXACT>;
+        case 80: return k_prefill_gemm_p<4, 5, DOTS, EXACT>;
+        case 96: return k_prefill_gemm_p<4, 6, DOTS, EXACT>;
+        case 112: return k_prefill_gemm_p<4, 7, DOTS, EXACT>;
+        case 128: return k_prefill_gemm_p<4, 8, DOTS, EXACT>;
+        case 160: return k_prefill_gemm_p<8, 5, DOTS, EXACT>;
+        case 192: return k_prefill_gemm_p<8, 6, DOTS, EXACT>;
         default: return nullptr;
     }
 }
@@ -753,7 +771,12 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
             forceN = e ? atoi(e) : 0;
         }
         const int N = forceN > 0 ? forceN : bestN;
-        GemmPKernel kern = dots ? gemm_p_kernel<true>(N) : gemm_p_kernel<false>(N);
+        static int exact = -1;
+        if (exact < 0) {
+            const char* e = getenv("QWEN_GEMM_EXACT"); // 0: fma fold (one rounding fewer per term)
+            exact = e ? atoi(e) : 1;
+        }
+        GemmPKernel kern = dots ? gemm_p_kernel<true, true>(N) : exact ? gemm_p_kernel<false, true>(N) : gemm_p_kernel<false, false>(N);
         if (!kern) {
             qw_set_error("prefill gemm: no kernel for %d weight rows per tile", N);
             return -2;
@@ -764,8 +787,9 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
         static bool attr_p = false;
         if (!attr_p) {
             for (int n_ : kPShapes) {
-                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<false>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
-                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<true>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<false, true>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<false, false>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<true, true>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
             }
             attr_p = true;
         }
@@ -778,8 +802,8 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
         }
         const bool prof_now = want_prof == 1 && prof_skip-- <= 0;
         if (prof_now && !prof) {
-            cudaMalloc((void**) &prof, 3 * 64 * 8 * 8);
-            cudaMemset(prof, 0, 3 * 64 * 8 * 8);
+            cudaMalloc((void**) &prof, (3 * 64 * 8 + 4 * 160) * 8);
+            cudaMemset(prof, 0, (3 * 64 * 8 + 4 * 160) * 8);
         }
         GemmPParams pp{xsT, out, dots, d, n, T, Tpad, tok_tiles, ((d + N - 1) / N) * tok_tiles, err_dev, prof_now ? prof : nullptr};
         const int grid = std::min(sms, pp.tiles);
@@ -789,9 +813,22 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
         if (prof_now) { // one dump per process
             want_prof = 2;
             cudaStreamSynchronize(st);
-            static long long h[3 * 64 * 8];
+            static long long h[3 * 64 * 8 + 4 * 160];
             cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
             const long long z = h[0];
+            {
+                const long long* c = h + 3 * 64 * 8;
+                long long t0 = c[0], t1 = 0, setup = 0, first = 0, last_end_min = 1ll << 62;
+                for (int b = 0; b < grid; ++b) {
+                    t0 = std::min(t0, c[4 * b]);
+                    t1 = std::max(t1, c[4 * b + 3]);
+                    last_end_min = std::min(last_end_min, c[4 * b + 3]);
+                    setup = std::max(setup, c[4 * b + 1] - c[4 * b]);
+                    first = std::max(first, c[4 * b + 2] - c[4 * b]);
+                }
+                fprintf(stderr, "[gemm prof] CTA spans (globaltimer ns): first start -> last end %lld, earliest end %lld, start skew %lld, setup <= %lld, first tile done <= %lld\n",
+                        t1 - t0, last_end_min - t0, [&] { long long m = 0; for (int b = 0; b < grid; ++b) m = std::max(m, c[4 * b] - t0); return m; }(), setup, first);
+            }
             fprintf(stderr, "[gemm prof] d=%d n=%d T=%d N=%d tiles=%d (cycles since the MMA issuer's first stamp)\n", d, n, T, N, pp.tiles);
             for (int i = 0; i < 20; ++i) {
                 const long long *m = h + i * 8, *pd = h + (64 + i) * 8, *ep = h + (128 + i) * 8;

@@ -499,12 +499,13 @@ def test_prefill_matches_reference_token_by_token(qlib, oracle, pkg, ckpt_dir, s
             tok = nxt
 
 
-@pytest.mark.parametrize("n_heads,n_kv_heads,pos0,T", [(4, 2, 0, 70), (8, 2, 37, 200), (2, 2, 130, 64), (16, 2, 0, 129), (3, 1, 5, 1)])
+@pytest.mark.parametrize("n_heads,n_kv_heads,pos0,T", [(4, 2, 0, 70), (8, 2, 37, 200), (2, 2, 130, 64), (16, 2, 0, 129), (3, 1, 5, 1), (4, 2, 700, 70), (2, 1, 0, 512)])
 @pytest.mark.parametrize("variant", [2, 1])
 def test_prefill_attention_kernels_match_reference_attention(qlib, oracle, n_heads, n_kv_heads, pos0, T, variant):
     """The chunk attention kernels (csrc/prefill.cu: tiled k_attn_prefill_t = 2, per-warp k_attn_prefill = 1) against the
     reference's attention() (src/forward.c:141-195) token by token on random q / K / V: causal window 0 .. pos0 + t, ragged
-    tiles, every GQA ratio the kernels take, a chunk that starts mid-tile (pos0 % 64 != 0). fp32 op tolerance."""
+    tiles, every GQA ratio the kernels take, a chunk that starts mid-tile (pos0 % 64 != 0), rows merged from up to five key
+    blocks (pos0 = 700). fp32 op tolerance."""
     if variant == 1 and n_heads // n_kv_heads not in (1, 2, 4, 8):
         pytest.skip("the per-warp kernel is instantiated for GQA ratios 1, 2, 4, 8")
     rng = np.random.default_rng(1000 * n_heads + pos0 + T)
