@@ -27,6 +27,7 @@
 // TMEM / shared-memory pipelines (2 -> 4 accumulators, 6 -> 12 stages), 128-byte SWIZZLE_128B operand rows
 // (two groups per stage) and prefetching the weight scales changed nothing or lost a few per cent.
 #include <algorithm>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
@@ -352,6 +353,16 @@ constexpr int kPTblSlots = 2;
 constexpr int kPTblBytes = 4 * kPMaxN * 4 + 4 * kPM * 4; // [4 groups][N weight scales] + [4 groups][128 activation scales]
 constexpr int kPSmem = kPStages * kPStageBytes + kPScSlots * kPScBytes + kPTblSlots * kPTblBytes + 1024;
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 struct GemmPParams {
     const float* xsT;      // [groups][Tpad]
     float* out;            // [T][d]
@@ -382,7 +393,7 @@ __device__ __forceinline__ void tmem_ld_unit<8>(uint32_t taddr, int (&v)[8]) {
 // U = columns per tcgen05.ld (4 for N <= 128, 8 above), UC = loads per epilogue warp and group: N = 4 * UC * U weight rows per
 // tile, everything about the tile shape a compile-time constant (a first version with run-time unit counts spent more
 // issue slots on predicates and index arithmetic than on the promotion: 347 instructions per 48 outputs).
-template <int U, int UC, bool DOTS, bool EXACT>
+template <int U, int UC, bool DOTS, bool EXACT, bool PROF>
 __global__ void __launch_bounds__(kPThreads, 1)
 k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_s, const GemmPParams p) {
@@ -402,7 +413,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t scfull0 = s_u32(&bars[2 * kPStages]), scempty0 = s_u32(&bars[2 * kPStages + kPScSlots]);
     const uint32_t tfull0 = s_u32(&bars[2 * kPStages + 2 * kPScSlots]), tempty0 = tfull0 + 8 * 4;
     const uint32_t wtfull0 = tempty0 + 8 * 4, wtempty0 = wtfull0 + 8 * kPTblSlots;
-    if (p.prof && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x] = (long long) g_ns();
+    if (PROF && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x] = (long long) g_ns();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kPStages; ++s) {
@@ -432,7 +443,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    if (p.prof && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 1] = (long long) g_ns();
+    if (PROF && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 1] = (long long) g_ns();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -450,7 +461,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         ++sc_it;
                     }
                     const uint32_t s = it % kPStages;
-                    long long* pr = (p.prof && blockIdx.x == 0 && it < 64) ? p.prof + (64 + it) * 8 : nullptr;
+                    long long* pr = (PROF && blockIdx.x == 0 && it < 64) ? p.prof + (64 + it) * 8 : nullptr;
                     if (pr) pr[0] = clock64();
                     if (!(ok = mb_wait(empty0 + 8 * s, ((it / kPStages) & 1) ^ 1, p.err, 1))) break;
                     if (pr) pr[1] = clock64();
@@ -462,30 +473,35 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_i8(kPM, N);
-            uint32_t it = 0;
-            bool ok = true;
-            for (int tile = blockIdx.x; tile < p.tiles && ok; tile += gridDim.x) {
-                for (int g = 0; g < groups; ++g, ++it) {
-                    const uint32_t s = it % kPStages, b = it % NBUF;
-                    long long* pr = (p.prof && blockIdx.x == 0 && it < 64) ? p.prof + it * 8 : nullptr;
-                    if (pr) pr[0] = clock64();
-                    if (!(ok = mb_wait(tempty0 + 8 * b, ((it / NBUF) & 1) ^ 1, p.err, 2))) break; // the epilogue has read this buffer
-                    if (pr) pr[1] = clock64();
-                    if (!(ok = mb_wait(full0 + 8 * s, (it / kPStages) & 1, p.err, 3))) break;      // operands landed
-                    if (pr) pr[2] = clock64();
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t base = s_u32(smem + (size_t) s * kPStageBytes);
+        // ------------------------------------------------------------ MMA issuer: the whole warp walks the loop (no divergent
+        // region around the uniform-datapath instructions), one elected lane issues; the shared-memory descriptors of a stage
+        // are the descriptors of stage 0 plus a constant
+        const uint32_t idesc = umma_idesc_i8(kPM, N);
+        const uint64_t da0 = umma_desc_sw64(s_u32(smem)), db0 = umma_desc_sw64(s_u32(smem) + kPABytes);
+        uint32_t it = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.tiles && ok; tile += gridDim.x) {
+            for (int g = 0; g < groups; ++g, ++it) {
+                const uint32_t s = it % kPStages, b = it % NBUF;
+                long long* pr = (PROF && blockIdx.x == 0 && it < 64 && lane == 0) ? p.prof + it * 8 : nullptr;
+                if (pr) pr[0] = clock64();
+                ok = mb_wait(tempty0 + 8 * b, ((it / NBUF) & 1) ^ 1, p.err, 2); // the epilogue has read this buffer
+                if (pr) pr[1] = clock64();
+                ok = ok && mb_wait(full0 + 8 * s, (it / kPStages) & 1, p.err, 3); // operands landed
+                if (pr) pr[2] = clock64();
+                if (!(ok = __all_sync(0xffffffffu, ok))) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t so = (uint64_t) ((s * (uint32_t) kPStageBytes) >> 4);
                     const uint32_t dcol = tmem_base + b * (uint32_t) N;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) // 64 codes = 2 x K32: D[token][row] (+)= X[token][k] * W[row][k]
-                        umma_i8(dcol, umma_desc_sw64(base + 32 * k), umma_desc_sw64(base + kPABytes + 32 * k), idesc, k);
+                    // 64 codes = 2 x K32: D[token][row] (+)= X[token][k] * W[row][k]; the second K32 slice sits 32 bytes further
+                    umma_i8(dcol, da0 + so, db0 + so, idesc, 0);
+                    umma_i8(dcol, da0 + so + 2, db0 + so + 2, idesc, 1);
                     umma_commit(empty0 + 8 * s);
                     umma_commit(tfull0 + 8 * b);
-                    if (pr) pr[3] = clock64();
                 }
+                __syncwarp();
+                if (pr) pr[3] = clock64();
             }
         }
     } else if (warp == 2 + kPEpiWarps) {
@@ -538,7 +554,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int c = 0; c < CW; ++c) acc[c] = 0.0f;
             for (int g = 0; g < groups; ++g, ++it) {
                 const int gk = g & 3;
-                long long* pr = (p.prof && blockIdx.x == 0 && it < 64 && warp == 2 && lane == 0) ? p.prof + (128 + it) * 8 : nullptr;
+                long long* pr = (PROF && blockIdx.x == 0 && it < 64 && warp == 2 && lane == 0) ? p.prof + (128 + it) * 8 : nullptr;
                 if (pr) pr[0] = clock64();
                 const uint32_t ts = sc_it % kPTblSlots;
                 if (gk == 0 && !(ok = mb_wait(wtfull0 + 8 * ts, (sc_it / kPTblSlots) & 1, p.err, 8))) break; // the scale table of groups g .. g + 3
@@ -612,7 +628,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 }
                 if (pr) pr[7] = clock64();
             }
-            if (p.prof && warp == 2 && lane == 0 && tile == (int) blockIdx.x) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 2] = (long long) g_ns();
+            if (PROF && warp == 2 && lane == 0 && tile == (int) blockIdx.x) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 2] = (long long) g_ns();
             if (ok && t_ok) { // the tile is done: the stores overlap the next tile's main loop
                 float* orow = p.out + (size_t) t * p.d + row0 + cbeg;
                 if (row0 + cbeg + CW <= p.d && (p.d & 3) == 0) {
@@ -628,25 +644,25 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (p.prof && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 3] = (long long) g_ns();
+    if (PROF && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x + 3] = (long long) g_ns();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 typedef void (*GemmPKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmPParams);
 // weight rows per tile -> kernel: N = 16 .. 128 in steps of 16 (U = 4), 160 and 192 (U = 8)
-template <bool DOTS, bool EXACT>
+template <bool DOTS, bool EXACT, bool PROF = false>
 GemmPKernel gemm_p_kernel(int N) {
     switch (N) {
-        case 16: return k_prefill_gemm_p<4, 1, DOTS, EXACT>;
-        case 32: return k_prefill_gemm_p<4, 2, DOTS, EXACT>;
-        case 48: return k_prefill_gemm_p<4, 3, DOTS, EXACT>;
-        case 64: return k_prefill_gemm_p<4, 4, DOTS, EXACT>;
-        case 80: return k_prefill_gemm_p<4, 5, DOTS, EXACT>;
-        case 96: return k_prefill_gemm_p<4, 6, DOTS, EXACT>;
-        case 112: return k_prefill_gemm_p<4, 7, DOTS, EXACT>;
-        case 128: return k_prefill_gemm_p<4, 8, DOTS, EXACT>;
-        case 160: return k_prefill_gemm_p<8, 5, DOTS, EXACT>;
-        case 192: return k_prefill_gemm_p<8, 6, DOTS, EXACT>;
+        case 16: return k_prefill_gemm_p<4, 1, DOTS, EXACT, PROF>;
+        case 32: return k_prefill_gemm_p<4, 2, DOTS, EXACT, PROF>;
+        case 48: return k_prefill_gemm_p<4, 3, DOTS, EXACT, PROF>;
+        case 64: return k_prefill_gemm_p<4, 4, DOTS, EXACT, PROF>;
+        case 80: return k_prefill_gemm_p<4, 5, DOTS, EXACT, PROF>;
+        case 96: return k_prefill_gemm_p<4, 6, DOTS, EXACT, PROF>;
+        case 112: return k_prefill_gemm_p<4, 7, DOTS, EXACT, PROF>;
+        case 128: return k_prefill_gemm_p<4, 8, DOTS, EXACT, PROF>;
+        case 160: return k_prefill_gemm_p<8, 5, DOTS, EXACT, PROF>;
+        case 192: return k_prefill_gemm_p<8, 6, DOTS, EXACT, PROF>;
         default: return nullptr;
     }
 }
@@ -771,12 +787,25 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
             forceN = e ? atoi(e) : 0;
         }
         const int N = forceN > 0 ? forceN : bestN;
+        static long long* prof = nullptr;
+        static int want_prof = -1;
+        static int prof_skip = 0; // QWEN_GEMM_PROF=k: dump the stamps of the k-th launch of the process
+        if (want_prof < 0) {
+            want_prof = getenv("QWEN_GEMM_PROF") ? 1 : 0;
+            prof_skip = want_prof ? std::max(0, atoi(getenv("QWEN_GEMM_PROF")) - 1) : 0;
+        }
+        const bool prof_now = want_prof == 1 && prof_skip-- <= 0;
+        if (prof_now && !prof) {
+            cudaMalloc((void**) &prof, (3 * 64 * 8 + 4 * 160) * 8);
+            cudaMemset(prof, 0, (3 * 64 * 8 + 4 * 160) * 8);
+        }
         static int exact = -1;
         if (exact < 0) {
             const char* e = getenv("QWEN_GEMM_EXACT"); // 0: fma fold (one rounding fewer per term)
             exact = e ? atoi(e) : 1;
         }
         GemmPKernel kern = dots ? gemm_p_kernel<true, true>(N) : exact ? gemm_p_kernel<false, true>(N) : gemm_p_kernel<false, false>(N);
+        if (prof_now && !dots) kern = gemm_p_kernel<false, true, true>(N); // the stamped instantiation (exact fold)
         if (!kern) {
             qw_set_error("prefill gemm: no kernel for %d weight rows per tile", N);
             return -2;
@@ -790,20 +819,9 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
                 QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<false, true>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
                 QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<false, false>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
                 QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<true, true>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+                QW_CUDA(cudaFuncSetAttribute((const void*) gemm_p_kernel<false, true, true>(n_), cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
             }
             attr_p = true;
-        }
-        static long long* prof = nullptr;
-        static int want_prof = -1;
-        static int prof_skip = 0; // QWEN_GEMM_PROF=k: dump the stamps of the k-th launch of the process
-        if (want_prof < 0) {
-            want_prof = getenv("QWEN_GEMM_PROF") ? 1 : 0;
-            prof_skip = want_prof ? std::max(0, atoi(getenv("QWEN_GEMM_PROF")) - 1) : 0;
-        }
-        const bool prof_now = want_prof == 1 && prof_skip-- <= 0;
-        if (prof_now && !prof) {
-            cudaMalloc((void**) &prof, (3 * 64 * 8 + 4 * 160) * 8);
-            cudaMemset(prof, 0, (3 * 64 * 8 + 4 * 160) * 8);
         }
         GemmPParams pp{xsT, out, dots, d, n, T, Tpad, tok_tiles, ((d + N - 1) / N) * tok_tiles, err_dev, prof_now ? prof : nullptr};
         const int grid = std::min(sms, pp.tiles);
@@ -825,6 +843,12 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
                     last_end_min = std::min(last_end_min, c[4 * b + 3]);
                     setup = std::max(setup, c[4 * b + 1] - c[4 * b]);
                     first = std::max(first, c[4 * b + 2] - c[4 * b]);
+                }
+                {
+                    std::vector<long long> sp;
+                    for (int b = 0; b < grid; ++b) sp.push_back(c[4 * b + 3] - c[4 * b]);
+                    std::sort(sp.begin(), sp.end());
+                    fprintf(stderr, "[gemm prof] per-CTA lifetime ns: min %lld p25 %lld median %lld p75 %lld max %lld\n", sp[0], sp[grid / 4], sp[grid / 2], sp[3 * grid / 4], sp[grid - 1]);
                 }
                 fprintf(stderr, "[gemm prof] CTA spans (globaltimer ns): first start -> last end %lld, earliest end %lld, start skew %lld, setup <= %lld, first tile done <= %lld\n",
                         t1 - t0, last_end_min - t0, [&] { long long m = 0; for (int b = 0; b < grid; ++b) m = std::max(m, c[4 * b] - t0); return m; }(), setup, first);
