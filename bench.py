@@ -355,7 +355,9 @@ def main():
                            "int8_tops": 2 * macs / best / 1e12, "peak_tops": peak_i8,
                            "frac": 2 * macs / best / 1e12 / peak_i8,
                            "peak_source": peak_i8_src,
-                           "note": "group-scaled GEMM: the fp32 promotion of every 64-wide group runs on the CUDA cores"}
+                           "note": ("whole 512-token prefill (GEMMs + attention + norm/quantise passes) over the layer GEMMs' int8 ops; the "
+                                    "group-scaled GEMM promotes every 64-wide group to fp32 on the CUDA cores (5 issue cycles per output and "
+                                    "group: ceiling ~20 % of the tensor peak for the GEMMs alone), profiles/r2_prefill_summary.md")}
     except Exception as e:  # never lose the decode number
         line["prefill"] = {"error": repr(e)}
     gm.close()

@@ -568,38 +568,41 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + b * (uint32_t) N + cbeg;
                 const unsigned long long xs2 = pack2(xsc, xsc);
-                // TMEM -> registers two loads (2 U columns) at a time, software-pipelined: the loads of chunk k + 1 are in flight
-                // while chunk k is promoted; the buffer goes back to the MMA issuer as soon as the last load has landed
-                constexpr int NCH = (UC + 1) / 2;
-                int v[2][2][U];
-                tmem_ld_unit<U>(taddr, v[0][0]);
-                if (1 < UC) tmem_ld_unit<U>(taddr + U, v[0][1]);
+                // TMEM -> registers 16 columns (CH loads) per round trip; the compiler keeps one chunk's registers, so the next
+                // chunk's loads are issued behind this chunk's arithmetic; the buffer goes back to the MMA issuer as soon as the
+                // last load has landed
+                constexpr int CH = 16 / U, NCH = (UC + CH - 1) / CH;
+                int v[2][CH][U];
+#pragma unroll
+                for (int h = 0; h < CH; ++h)
+                    if (h < UC) tmem_ld_unit<U>(taddr + h * U, v[0][h]);
 #pragma unroll
                 for (int k = 0; k < NCH; ++k) {
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (pr && k < 2) pr[3 + k] = clock64();
                     if (k + 1 < NCH) {
-                        tmem_ld_unit<U>(taddr + (2 * k + 2) * U, v[(k + 1) & 1][0]);
-                        if (2 * k + 3 < UC) tmem_ld_unit<U>(taddr + (2 * k + 3) * U, v[(k + 1) & 1][1]);
+#pragma unroll
+                        for (int h = 0; h < CH; ++h)
+                            if ((k + 1) * CH + h < UC) tmem_ld_unit<U>(taddr + ((k + 1) * CH + h) * U, v[(k + 1) & 1][h]);
                     } else {
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mb_arrive(tempty0 + 8 * b);
                     }
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (2 * k + h < UC) {
+                    for (int h = 0; h < CH; ++h) {
+                        if (k * CH + h < UC) {
                             const int (&vv)[U] = v[k & 1][h];
                             if (DOTS && t_ok) { // test hook: a separate instantiation, the product kernel carries no such code
 #pragma unroll
                                 for (int e = 0; e < U; ++e) {
-                                    const int row = row0 + cbeg + (2 * k + h) * U + e;
+                                    const int row = row0 + cbeg + (k * CH + h) * U + e;
                                     if (row < p.d) p.dots[((size_t) t * p.d + row) * groups + g] = vv[e];
                                 }
                             }
 #pragma unroll
                             for (int e = 0; e < U; e += 4) {
-                                const int c = (2 * k + h) * U + e;
+                                const int c = (k * CH + h) * U + e;
                                 const float4 w4 = *reinterpret_cast<const float4*>(wg + c);
                                 float lo, hi;
                                 if (EXACT) { // two packed multiplies, scalar adds (see the note at mul2): the reference's three roundings
@@ -649,7 +652,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 }
 
 typedef void (*GemmPKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmPParams);
-// weight rows per tile -> kernel: N = 16 .. 128 in steps of 16 (U = 4), 160 and 192 (U = 8)
+// weight rows per tile -> kernel: N = 16 .. 192 in steps of 16 (U = 4 columns per tcgen05.ld, or 8 where N / 4 is a multiple of 8)
 template <bool DOTS, bool EXACT, bool PROF = false>
 GemmPKernel gemm_p_kernel(int N) {
     switch (N) {
@@ -661,12 +664,14 @@ GemmPKernel gemm_p_kernel(int N) {
         case 96: return k_prefill_gemm_p<4, 6, DOTS, EXACT, PROF>;
         case 112: return k_prefill_gemm_p<4, 7, DOTS, EXACT, PROF>;
         case 128: return k_prefill_gemm_p<4, 8, DOTS, EXACT, PROF>;
+        case 144: return k_prefill_gemm_p<4, 9, DOTS, EXACT, PROF>;
         case 160: return k_prefill_gemm_p<8, 5, DOTS, EXACT, PROF>;
+        case 176: return k_prefill_gemm_p<4, 11, DOTS, EXACT, PROF>;
         case 192: return k_prefill_gemm_p<8, 6, DOTS, EXACT, PROF>;
         default: return nullptr;
     }
 }
-constexpr int kPShapes[] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192};
+constexpr int kPShapes[] = {16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 176, 192};
 
 // Measured int8 tensor peak (MEASURED_PEAKS.json has no int8 figure, "the builder must measure it on the
 // box"): every CTA issues `iters` back-to-back tcgen05.mma.cta_group::1.kind::i8 M128 N256 K32 on resident shared-memory
