@@ -186,6 +186,15 @@ int qwen_cuda_matmul_batch(float* out, int32_t* dots, const int8_t* xq, const fl
  * tcgen05.mma.kind::i8 M128 N256 K32 per SM on resident operands, best of `reps` runs. bench.py's prefill fraction is
  * quoted against this number, not the nominal 4.5 POPS. */
 int qwen_cuda_int8_peak(int iters, int reps, float* tops);
+
+/* Test hooks of the prefill kernels (csrc/prefill.cu, csrc/prefill_gemm.cu).
+ * debug_attn_prefill: the chunk attention kernels on host data -- q [T][n_heads][128], k / v [pos0 + T][n_kv_heads * 128]
+ * (the reference's cache layout, src/forward.c:141-195), out [T][n_heads][128]; variant 1 = per-warp kernel, 2 = tiled kernel.
+ * debug_attn_plan / debug_gemm_plan: host-only (no GPU): the fixed key blocks of the chunk attention and the GEMM tile shape. */
+int qwen_cuda_debug_attn_prefill(float* out, const float* q, const float* k, const float* v, int n_heads, int n_kv_heads, int pos0,
+                                 int T, int variant);
+int qwen_cuda_debug_attn_plan(int pos0, int T, int* parts, int* k01, int max_parts);
+int qwen_cuda_debug_gemm_plan(int d, int T, int sms, int* tiles);
 int qwen_cuda_rmsnorm(float* out, const float* x, const float* w, int size);                /* forward.c:12-28 */
 int qwen_cuda_softmax(float* x, int size);                                                  /* forward.c:34-77 */
 /* cos/sin: head_dim/2 host-computed values for this position (forward.c:109-110). */

@@ -738,3 +738,18 @@ extern "C" int qwen_cuda_debug_attn_prefill(float* out, const float* q, const fl
     cudaFree(dq); cudaFree(dk); cudaFree(dv); cudaFree(dout);
     return rc;
 }
+
+// Host-only test hook (no GPU needed): the fixed key blocks of the chunk attention. For a chunk of T tokens at pos0 fills,
+// per query tile qt (ascending), parts[qt] and the blocks' key-tile ranges k01[qt][part][2] (at most max_parts per tile).
+// Returns the number of query tiles, or a negative value.
+extern "C" int qwen_cuda_debug_attn_plan(int pos0, int T, int* parts, int* k01, int max_parts) {
+    if (pos0 < 0 || T <= 0 || T > kChunkTokens || !parts || !k01 || max_parts <= 0) return -2;
+    const AttnPlan pl = attn_plan(pos0, T);
+    for (int i = 0; i < pl.nq; ++i) {
+        const int qt = pl.nq - 1 - i;
+        parts[qt] = pl.parts[i];
+        if (pl.parts[i] > max_parts) return -3;
+        for (int p = 0; p < pl.parts[i]; ++p) attn_part_range(p, k01[(qt * max_parts + p) * 2], k01[(qt * max_parts + p) * 2 + 1]);
+    }
+    return pl.nq;
+}

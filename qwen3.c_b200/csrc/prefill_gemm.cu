@@ -672,6 +672,21 @@ GemmPKernel gemm_p_kernel(int N) {
     }
 }
 constexpr int kPShapes[] = {16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 176, 192};
+// weight rows per tile for a d-row matrix and tok_tiles token tiles on `sms` SMs: minimise rounds x (N + a per-group fixed
+// cost worth ~24 rows), rounds = ceil(tiles / SMs); ties go to the smaller N (more SMs busy)
+int gemm_tile_rows(int d, int tok_tiles, int sms) {
+    int bestN = 16;
+    long best = -1;
+    for (int N : kPShapes) {
+        const long tiles = (long) ((d + N - 1) / N) * tok_tiles, rounds = (tiles + sms - 1) / sms;
+        const long cost = rounds * (N + 24);
+        if (best < 0 || cost < best) {
+            best = cost;
+            bestN = N;
+        }
+    }
+    return bestN;
+}
 
 // Measured int8 tensor peak (MEASURED_PEAKS.json has no int8 figure, "the builder must measure it on the
 // box"): every CTA issues `iters` back-to-back tcgen05.mma.cta_group::1.kind::i8 M128 N256 K32 on resident shared-memory
@@ -773,19 +788,9 @@ int qw_prefill_gemm(const uint8_t* w, const int8_t* xq, const float* xsT, float*
         QW_CUDA(cudaEventCreate(&e1));
     }
     if (variant != 1) {
-        // Persistent kernel: pick the weight rows per tile N that minimises rounds x (N + a per-group fixed cost worth ~24
-        // rows), rounds = ceil(tiles / SMs); ties go to the smaller N (more SMs busy).
+        // Persistent kernel: weight rows per tile chosen so that the tiles fill whole rounds of SMs (gemm_tile_rows)
         const int tok_tiles = (T + kPM - 1) / kPM;
-        int bestN = 16;
-        long best = -1;
-        for (int N : kPShapes) {
-            const long tiles = (long) ((d + N - 1) / N) * tok_tiles, rounds = (tiles + sms - 1) / sms;
-            const long cost = rounds * (N + 24);
-            if (best < 0 || cost < best) {
-                best = cost;
-                bestN = N;
-            }
-        }
+        const int bestN = gemm_tile_rows(d, tok_tiles, sms);
         static int forceN = -1;
         if (forceN < 0) {
             const char* e = getenv("QWEN_GEMM_N");
@@ -1011,4 +1016,14 @@ extern "C" int qwen_cuda_int8_peak(int iters, int reps, float* tops) {
     }
     *tops = (float) (2.0 * 128 * 256 * 32 * (double) iters * sms / (best * 1e-3) / 1e12);
     return 0;
+}
+
+// Host-only test hook (no GPU needed): the tile shape qw_prefill_gemm picks for a d-row matrix and T tokens on `sms` SMs.
+// Returns the weight rows per tile N; *tiles = row tiles x token tiles.
+extern "C" int qwen_cuda_debug_gemm_plan(int d, int T, int sms, int* tiles) {
+    if (d <= 0 || T <= 0 || sms <= 0) return -2;
+    const int tok_tiles = (T + kPM - 1) / kPM;
+    const int N = gemm_tile_rows(d, tok_tiles, sms);
+    if (tiles) *tiles = ((d + N - 1) / N) * tok_tiles;
+    return N;
 }

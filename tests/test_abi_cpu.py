@@ -108,3 +108,50 @@ def test_product_sources_never_touch_the_oracle():
             if f.endswith((".py", ".c", ".cu", ".cuh", ".h", "Makefile")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_prefill_attention_key_blocks_are_a_fixed_partition(qlib):
+    """Host logic of the chunk attention (csrc/prefill.cu, no GPU needed): a query tile's visible key tiles are covered by
+    its blocks exactly once, and a block's range depends on its index only -- so every row is merged over the same
+    absolute blocks however the prompt is cut into calls (the invariant test_prefill_in_two_calls_equals_one_call checks
+    on the GPU)."""
+    import ctypes as C
+    lib = qlib.lib
+    lib.qwen_cuda_debug_attn_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    MAXP = 40
+    seen = {}
+    for pos0, T in [(0, 1), (0, 64), (0, 65), (0, 512), (33, 37), (130, 64), (700, 70), (3584, 512), (16000, 300)]:
+        parts = (C.c_int * 8)()
+        k01 = (C.c_int * (8 * MAXP * 2))()
+        nq = lib.qwen_cuda_debug_attn_plan(pos0, T, parts, k01, MAXP)
+        assert nq == (T + 63) // 64
+        for qt in range(nq):
+            last_pos = pos0 + min(T, (qt + 1) * 64) - 1
+            nkt = last_pos // 64 + 1
+            nxt = 0
+            for p in range(parts[qt]):
+                k0, k1 = k01[(qt * MAXP + p) * 2], k01[(qt * MAXP + p) * 2 + 1]
+                assert k0 == nxt and k1 > k0  # contiguous, no overlap
+                assert seen.setdefault(p, (k0, k1)) == (k0, k1)  # a function of the block index alone
+                nxt = k1
+            assert nxt >= nkt and k01[(qt * MAXP + parts[qt] - 1) * 2] < nkt  # covers the visible tiles, no empty last block
+    assert lib.qwen_cuda_debug_attn_plan(0, 513, (C.c_int * 8)(), (C.c_int * 16)(), 1) < 0  # more than one chunk
+
+
+def test_prefill_gemm_tile_shape_fills_rounds_of_sms(qlib):
+    """Host logic of the persistent prefill GEMM (csrc/prefill_gemm.cu, no GPU needed): the weight rows per tile are a
+    multiple of 16 within the instantiated shapes, the tiles cover the matrix, and on the BASELINE shapes the tile count
+    wastes less than a fifth of the last round of 148 SMs."""
+    import ctypes as C
+    lib = qlib.lib
+    lib.qwen_cuda_debug_gemm_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    for d, T in [(6144, 512), (19456, 512), (2560, 512), (4096, 512), (12288, 512), (2048, 512), (8, 1), (300, 200), (51200, 512), (5120, 2048)]:
+        tiles = C.c_int(0)
+        N = lib.qwen_cuda_debug_gemm_plan(d, T, 148, C.byref(tiles))
+        assert 16 <= N <= 192 and N % 16 == 0
+        tok_tiles = (T + 127) // 128
+        assert tiles.value == -(-d // N) * tok_tiles and -(-d // N) * N >= d
+        if d >= 2048 and T >= 512:
+            rounds = -(-tiles.value // 148)
+            assert tiles.value / (rounds * 148) > 0.8, (d, T, N, tiles.value)
+    assert lib.qwen_cuda_debug_gemm_plan(0, 1, 148, None) < 0
