@@ -305,9 +305,11 @@ k_attn_prefill_t(const float* __restrict__ q, const float* __restrict__ k_layer,
     const int t0 = qt * kTQ;
     const int rows = min(kTQ, T - t0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the Q tile travels with the first K tile (same cp.async group)
     for (int i = tid; i < kTQ * 32; i += 128) {
         const int r = i >> 5, c = (i & 31) * 4;
-        *reinterpret_cast<float4*>(sQ + r * 128 + c) = r < rows ? *reinterpret_cast<const float4*>(q + ((size_t) (t0 + r) * Hl + h) * 128 + c) : zero4;
+        if (r < rows) cp_async16(sQ + r * 128 + c, q + ((size_t) (t0 + r) * Hl + h) * 128 + c);
+        else *reinterpret_cast<float4*>(sQ + r * 128 + c) = zero4;
     }
     const float* K = k_layer + (size_t) kvh * S * 128;
     const float* V = v_layer + (size_t) kvh * S * 128;
@@ -500,6 +502,73 @@ k_attn_merge(const float* __restrict__ partial, float* __restrict__ out, int Hl,
     out[((size_t) t * Hl + h) * 128 + d] = __fdiv_rn(A, L);
 }
 
+// k_attn_merge and the Q8_0 quantiser of the attention output (the input of wo) in one pass: one block per token, a warp per
+// head (lane = 4 output dims), rows of unsplit query tiles are read from `att`, rows of split ones merged from the partials
+// with k_attn_merge's arithmetic (same order, same roundings); then the quantiser of k_prep_quant (a half-warp per group).
+__global__ void __launch_bounds__(256)
+k_attn_merge_quant(const float* __restrict__ partial, const float* __restrict__ att, int8_t* __restrict__ q8, float* __restrict__ xsT,
+                   int Hl, int pos0, int T, int Tpad) {
+    const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qt = t / kTQ;
+    const int last_pos = pos0 + min(T, (qt + 1) * kTQ) - 1;
+    const int np = attn_parts(last_pos / kTK + 1);
+    const size_t pstride = (size_t) T * Hl * kTPartStride;
+    const int n = Hl * 128;
+    for (int h = warp; h < Hl; h += 8) {
+        float v[4];
+        if (np == 1) {
+            const float4 a4 = *reinterpret_cast<const float4*>(att + ((size_t) t * Hl + h) * 128 + lane * 4);
+            v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w;
+        } else {
+            const float* base = partial + ((size_t) t * Hl + h) * kTPartStride;
+            float A[4] = {0.f, 0.f, 0.f, 0.f}, L = 0.0f;
+            if (np <= 4) { // contexts up to 512: every load issued before the first use
+                float mp[4], lp[4];
+                float4 o4[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const bool live = p < np;
+                    mp[p] = live ? base[p * pstride + 128] : -INFINITY;
+                    lp[p] = live ? base[p * pstride + 129] : 0.0f;
+                    o4[p] = live ? *reinterpret_cast<const float4*>(base + p * pstride + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const float M = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    if (mp[p] == -INFINITY) continue; // a block this row sees nothing of
+                    const float w = expf(__fsub_rn(mp[p], M));
+                    L = __fmaf_rn(lp[p], w, L);
+                    A[0] = __fmaf_rn(o4[p].x, w, A[0]); A[1] = __fmaf_rn(o4[p].y, w, A[1]);
+                    A[2] = __fmaf_rn(o4[p].z, w, A[2]); A[3] = __fmaf_rn(o4[p].w, w, A[3]);
+                }
+            } else {
+                float M = -INFINITY;
+                for (int p = 0; p < np; ++p) M = fmaxf(M, base[p * pstride + 128]);
+                for (int p = 0; p < np; ++p) {
+                    const float* src = base + p * pstride;
+                    const float mp = src[128];
+                    if (mp == -INFINITY) continue;
+                    const float w = expf(__fsub_rn(mp, M));
+                    const float4 o4 = *reinterpret_cast<const float4*>(src + lane * 4);
+                    L = __fmaf_rn(src[129], w, L);
+                    A[0] = __fmaf_rn(o4.x, w, A[0]); A[1] = __fmaf_rn(o4.y, w, A[1]);
+                    A[2] = __fmaf_rn(o4.z, w, A[2]); A[3] = __fmaf_rn(o4.w, w, A[3]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __fdiv_rn(A[e], L);
+        }
+        float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o)); // within the half-warp = one group of 64
+        const float scale = q8_scale(amax);
+        const int c0 = q8_code(v[0], scale), c1 = q8_code(v[1], scale), c2 = q8_code(v[2], scale), c3 = q8_code(v[3], scale);
+        *reinterpret_cast<uint32_t*>(q8 + (size_t) t * n + h * 128 + lane * 4) =
+            (uint32_t) (c0 & 0xff) | ((uint32_t) (c1 & 0xff) << 8) | ((uint32_t) (c2 & 0xff) << 16) | ((uint32_t) (c3 & 0xff) << 24);
+        if ((lane & 15) == 0) xsT[(size_t) (2 * h + (lane >> 4)) * Tpad + t] = scale;
+    }
+}
+
 // residual add over a chunk (forward.c:295-298, 335-338)
 __global__ void k_add_rows(float* __restrict__ x, const float* __restrict__ y, size_t n) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -592,13 +661,8 @@ static int prefill_chunk(QwenCudaCtx* c, PrefillBufs* pb, const int* tokens_host
             }
             k_attn_prefill_t<<<(unsigned) (plan.first[plan.nq] * c->Hl), 128, kTSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att,
                                                                                           pb->apart, c->Hl, kv_mul, c->S, pos0, T, plan);
-            if (maxparts > 1) {
-                int i_split = 0; // query tiles are listed latest first: the last one with parts > 1 is the earliest split tile
-                for (int i = 0; i < plan.nq; ++i)
-                    if (plan.parts[i] > 1) i_split = i;
-                const int t_first = (plan.nq - 1 - i_split) * kTQ;
-                k_attn_merge<<<dim3((unsigned) (T - t_first), (unsigned) c->Hl), 128, 0, st>>>(pb->apart, pb->att, c->Hl, pos0, T, t_first);
-            }
+            // merge of the split rows + the quantiser of the attention output in one pass
+            k_attn_merge_quant<<<T, 256, 0, st>>>(pb->apart, pb->att, pb->q8, pb->xsT, c->Hl, pos0, T, Tpad);
         } else
         switch (kv_mul) {
             case 1: k_attn_prefill<1><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
@@ -607,7 +671,7 @@ static int prefill_chunk(QwenCudaCtx* c, PrefillBufs* pb, const int* tokens_host
             case 8: k_attn_prefill<8><<<ag, 256, kAttnSmem, st>>>(pb->q, c->k_cache + loff, c->v_cache + loff, pb->att, c->Hl, c->S, pos0, T); break;
             default: qw_set_error("prefill: unsupported GQA ratio %d", kv_mul); return -2;
         }
-        k_prep_quant<<<T, 256, 0, st>>>(pb->att, nullptr, nullptr, pb->q8, pb->xsT, Pl, Tpad, 0);
+        if (attn_v == 1) k_prep_quant<<<T, 256, 0, st>>>(pb->att, nullptr, nullptr, pb->q8, pb->xsT, Pl, Tpad, 0);
         if (gemm(c->w_o + l * c->w_o_stride, pb->xa, D, Pl)) return -1;
         if (qw_tp_allreduce(c, pb->xa, TD)) return -1; // wo is row-parallel under tensor parallelism
         // feed-forward block (forward.c:303-338); x += wo output inside the norm + quantise pass
