@@ -351,7 +351,9 @@ constexpr int kPEpiWarps = 16;
 constexpr int kPThreads = 32 * (3 + kPEpiWarps); // producer, MMA issuer, 16 epilogue warps, scale warp
 constexpr int kPTblSlots = 2;
 constexpr int kPTblBytes = 4 * kPMaxN * 4 + 4 * kPM * 4; // [4 groups][N weight scales] + [4 groups][128 activation scales]
-constexpr int kPSmem = kPStages * kPStageBytes + kPScSlots * kPScBytes + kPTblSlots * kPTblBytes + 1024;
+constexpr int kPBarOff = kPStages * kPStageBytes + kPScSlots * kPScBytes + kPTblSlots * kPTblBytes; // mbarriers + the TMEM base word
+constexpr int kPBars = 2 * kPStages + 2 * kPScSlots + 2 * 4 + 2 * kPTblSlots;
+constexpr int kPSmem = kPBarOff + 8 * kPBars + 16 + 1024;
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -405,13 +407,14 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sc_ring = smem + (size_t) kPStages * kPStageBytes;
     uint8_t* tbl_ring = sc_ring + kPScSlots * kPScBytes;
-    __shared__ __align__(8) uint64_t bars[2 * kPStages + 2 * kPScSlots + 2 * 4 + 2 * kPTblSlots];
-    __shared__ uint32_t tmem_base_s;
+    // the barriers live in the dynamic shared memory too: their addresses are the (register-resident) base plus constants. As a
+    // static __shared__ array ptxas rebuilt their window address from SR_CgaCtaId (an S2R, tens of cycles) in front of every wait.
+    volatile uint32_t& tmem_base_s = *reinterpret_cast<volatile uint32_t*>(smem + kPBarOff + 8 * kPBars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = p.n / 64;
-    const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kPStages]);
-    const uint32_t scfull0 = s_u32(&bars[2 * kPStages]), scempty0 = s_u32(&bars[2 * kPStages + kPScSlots]);
-    const uint32_t tfull0 = s_u32(&bars[2 * kPStages + 2 * kPScSlots]), tempty0 = tfull0 + 8 * 4;
+    const uint32_t full0 = s_u32(smem) + kPBarOff, empty0 = full0 + 8 * kPStages;
+    const uint32_t scfull0 = empty0 + 8 * kPStages, scempty0 = scfull0 + 8 * kPScSlots;
+    const uint32_t tfull0 = scempty0 + 8 * kPScSlots, tempty0 = tfull0 + 8 * 4;
     const uint32_t wtfull0 = tempty0 + 8 * 4, wtempty0 = wtfull0 + 8 * kPTblSlots;
     if (PROF && threadIdx.x == 0) p.prof[3 * 64 * 8 + 4 * blockIdx.x] = (long long) g_ns();
 
@@ -436,7 +439,7 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "n"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(full0 + 8 * kPBars), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
