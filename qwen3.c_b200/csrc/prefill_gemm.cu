@@ -488,11 +488,11 @@ k_prefill_gemm_p(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 const uint32_t s = it % kPStages, b = it % NBUF;
                 long long* pr = (PROF && blockIdx.x == 0 && it < 64 && lane == 0) ? p.prof + it * 8 : nullptr;
                 if (pr) pr[0] = clock64();
-                ok = mb_wait(tempty0 + 8 * b, ((it / NBUF) & 1) ^ 1, p.err, 2); // the epilogue has read this buffer
+                // every lane waits on the same barriers, so `ok` is warp-uniform except after a time-out (then the launch is lost anyway)
+                if (!(ok = mb_wait(tempty0 + 8 * b, ((it / NBUF) & 1) ^ 1, p.err, 2))) break; // the epilogue has read this buffer
                 if (pr) pr[1] = clock64();
-                ok = ok && mb_wait(full0 + 8 * s, (it / kPStages) & 1, p.err, 3); // operands landed
+                if (!(ok = mb_wait(full0 + 8 * s, (it / kPStages) & 1, p.err, 3))) break;     // operands landed
                 if (pr) pr[2] = clock64();
-                if (!(ok = __all_sync(0xffffffffu, ok))) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint64_t so = (uint64_t) ((s * (uint32_t) kPStageBytes) >> 4);
