@@ -214,6 +214,38 @@ def _timed(fn):
     return time.perf_counter() - t0
 
 
+def cli_generation(pkg, path, shape):
+    """SURVEY.md 8f-2 at program level: the reference's own CLI (examples/qwen.c + src/completion.c with
+    integration/completion_fast.patch: prompt through forward_prefill, sampling on the device), linked against libqwen3.so
+    (oracle/_ref/qwen_b200_fast, built by oracle/Makefile where the reference tree is present). Two runs with the same
+    64-token prompt and seed at context 192 and 704: start-up, model load and the prefill cancel in the difference, which is
+    512 generated tokens (the synthetic tokenizer has no stop token, so generation runs to the end of the context)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "qwen_b200_fast")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/qwen_b200_fast not built (needs the reference tree at build time)"}
+    if not os.path.exists(path + ".tokenizer"):
+        pkg.checkpoint.write_tokenizer(path + ".tokenizer", shape.vocab_size)
+    prompt = "the quick brown fox jumps over the lazy dog. " * 2
+    prompt = prompt[:64]
+    times = {}
+    for ctx in (192, 704):
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, path, "-m", "completion", "-i", prompt, "-c", str(ctx), "-t", "0.7", "-p", "0.8", "-s", "1"],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"error": "exit %d: %s" % (r.returncode, r.stderr[-300:].decode(errors="replace"))}
+            best = dt if best is None else min(best, dt)
+        times[ctx] = best
+    gen = 704 - 192
+    return {"value": gen / (times[704] - times[192]), "unit": "tok/s", "generated_tokens": gen, "prompt_tokens": len(prompt),
+            "wall_s": {str(k): v for k, v in times.items()},
+            "what": "reference CLI + completion_fast.patch on libqwen3.so, -m completion -t 0.7 -p 0.8: wall-time difference of two "
+                    "runs (context 704 vs 192), i.e. model load, CUDA start-up and the prompt prefill cancel"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,6 +393,11 @@ def main():
     except Exception as e:  # never lose the decode number
         line["prefill"] = {"error": repr(e)}
     gm.close()
+    if workload == "4b-decode-ctx4096" and not args.no_tp_base:
+        try:  # (4) the reference's own program on this library (patched generation loops)
+            line["cli"] = cli_generation(pkg, path, shape)
+        except Exception as e:
+            line["cli"] = {"error": repr(e)}
     if workload == "4b-decode-ctx4096" and not args.no_tp_base:
         # the tensor-parallel lines (N >= 2) run the 8B shape: its one-GPU figure, so that the 1 -> 8 curve divides like by like
         try:
