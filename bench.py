@@ -246,6 +246,45 @@ def cli_generation(pkg, path, shape):
                     "runs (context 704 vs 192), i.e. model load, CUDA start-up and the prompt prefill cancel"}
 
 
+def config2_job(pkg, ql):
+    """BASELINE config 2 as one job on one GPU: Qwen3-1.7B shape, a 512-token prompt through forward_prefill, then 256 decode
+    steps (sampled on the device, token fed back) -- wall time of the whole job from host tokens in to the last token out."""
+    shape_name = "1.7b"
+    shape = pkg.checkpoint.SHAPES[shape_name]
+    path = ensure_ckpt(pkg, shape_name)
+    Tp, Tg = 512, 256
+    toks = [int(t) for t in np.random.default_rng(1).integers(0, shape.vocab_size, size=Tp)]
+    state = [np.uint64(0x9E3779B97F4A7C15)]
+
+    def coin():  # xorshift* as in the reference's sampler
+        x = int(state[0])
+        x ^= x >> 12
+        x ^= (x << 25) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 27
+        state[0] = np.uint64(x)
+        return float(np.float32(((x * 0x2545F4914F6CDD1D & 0xFFFFFFFFFFFFFFFF) >> 32 >> 8) / 16777216.0))
+
+    gm = ql.open(path, Tp + Tg + 8)
+    try:
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            lg = gm.forward_prefill(toks, 0)
+            t1 = time.perf_counter()
+            tok = int(np.argmax(lg))
+            for i in range(Tg):
+                gm.forward_async(tok, Tp + i)
+                tok = gm.sample(0.7, 0.8, coin()) or 7
+            t2 = time.perf_counter()
+            if best is None or t2 - t0 < best[0]:
+                best = (t2 - t0, t1 - t0, t2 - t1)
+    finally:
+        gm.close()
+    return {"workload": "1.7b-prefill512+decode256", "job_s": best[0], "prefill_ms": 1e3 * best[1], "prefill_tok_s": Tp / best[1],
+            "decode_tok_s": Tg / best[2], "tok_s_overall": (Tp + Tg) / best[0],
+            "what": "forward_prefill (logits of the last prompt token to the host) then forward_async + qwen_cuda_sample per token; best of 3"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -398,6 +437,10 @@ def main():
             line["cli"] = cli_generation(pkg, path, shape)
         except Exception as e:
             line["cli"] = {"error": repr(e)}
+        try:  # (5) BASELINE config 2 as one job
+            line["config2"] = config2_job(pkg, ql)
+        except Exception as e:
+            line["config2"] = {"error": repr(e)}
     if workload == "4b-decode-ctx4096" and not args.no_tp_base:
         # the tensor-parallel lines (N >= 2) run the 8B shape: its one-GPU figure, so that the 1 -> 8 curve divides like by like
         try:
