@@ -1596,6 +1596,10 @@ int qw_mega_init(QwenCudaCtx* c) {
         return -1;
     }
     st->grid = std::min(c->num_sms, kMaxGrid);
+    if (const char* e = getenv("QWEN_MEGA_GRID")) { // experiment: fewer CTAs (small shapes are bound by the hand-offs, not by streaming)
+        const int v = atoi(e);
+        if (v > 0) st->grid = std::min(st->grid, v);
+    }
     if (st->grid < c->KVHl) { // every kv head needs a block of its own (attn_split)
         st->grid = 0;
         c->path = 1;
