@@ -13,6 +13,10 @@
 //
 // Chunks of kChunkTokens tokens bound the activation memory; chunk c attends over the cache rows of the
 // earlier chunks plus its own causal part.
+//
+// Per layer and chunk (round 2): k_prep_quant (norm + quantise, previous residual add fused) -> qkv GEMM -> k_qkv_post_rows ->
+// k_attn_prefill_t (tiled fp32 attention in fixed key blocks) -> k_attn_merge_quant (merge of split rows + quantiser) -> wo GEMM
+// -> k_prep_quant (residual add + norm + quantise) -> w1/w3 GEMM -> k_prep_quant (SwiGLU + quantise) -> w2 GEMM.
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>

@@ -10,7 +10,11 @@
 // ((float) dot * ws) * xs and the terms are folded into an fp32 accumulator left to right in group
 // order -- so every output is BIT-IDENTICAL to the reference matmul of that token.
 //
-// Structure (one CTA per 128 weight rows x 128 tokens tile, warp specialised):
+// Two kernels live here. k_prefill_gemm_p (further down) is the one forward_prefill uses: persistent, tokens on the UMMA M
+// dimension, tile shapes that fill whole rounds of SMs. k_prefill_gemm is the round-1 kernel, kept selectable (QWEN_GEMM_V=1)
+// and as the reference point of profiles/r2_prefill_summary.md. Both produce the same bits.
+//
+// Structure of k_prefill_gemm (one CTA per 128 weight rows x 128 tokens tile, warp specialised):
 //   warp 0  : TMA producer. Per group: a 128-row x 64-byte box of W straight out of the SG layout
 //             (cp.async.bulk.tensor.2d, SWIZZLE_64B), the matching 128-token x 64-byte box of the
 //             int8 activations, and the 128 activation scales of the group (bulk copy).
